@@ -1,0 +1,121 @@
+"""ctypes binding of `libcastergvp.so` (the C ABI declared in `include/castergvp.h`).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C caster_dta_b200/csrc`.  There is NO fallback:
+if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+MAX_CHAIN = 4
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+AGGR_SUM, AGGR_MEAN = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcastergvp.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class GvpDesc(C.Structure):
+    _fields_ = [("si", C.c_int32), ("vi", C.c_int32), ("so", C.c_int32), ("vo", C.c_int32), ("h", C.c_int32),
+                ("scalar_act", C.c_int32), ("vector_act", C.c_int32), ("vector_gate", C.c_int32)]
+
+
+class GvpWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wh", "ws", "bs", "wv", "wsv", "bg")]
+
+
+class GvpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wh", "ws", "bs", "wv", "wsv", "bg")]
+
+
+class Plan(C.Structure):
+    _fields_ = [("num_edges", C.c_int64), ("num_nodes", C.c_int64)] + \
+               [(n, C.c_void_p) for n in ("perm", "src", "dst", "rowptr", "sperm", "srowptr")]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("ns", C.c_int32), ("nv", C.c_int32), ("es", C.c_int32), ("ev", C.c_int32), ("n_gvp", C.c_int32),
+                ("gvp", GvpDesc * MAX_CHAIN), ("aggr", C.c_int32), ("edge_sorted", C.c_int32)]
+
+
+class RowDesc(C.Structure):
+    _fields_ = [("in_s", C.c_int32), ("in_v", C.c_int32), ("onehot", C.c_int32), ("has_residual_in", C.c_int32),
+                ("pre_norm", C.c_int32), ("n_gvp", C.c_int32), ("gvp", GvpDesc * MAX_CHAIN),
+                ("post_residual", C.c_int32), ("post_norm", C.c_int32)]
+
+
+class RowArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "in_s", "in_v", "types", "in_index", "h_s", "h_v", "mask0_s", "mask0_v", "mask1_s", "mask1_v",
+        "ln0_w", "ln0_b", "ln1_w", "ln1_b", "h_packed", "out_s", "out_v")]
+
+
+class RowGradArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_out_s", "d_out_v", "d_in_s", "d_in_v", "d_h_s", "d_h_v", "d_ln0_w", "d_ln0_b", "d_ln1_w", "d_ln1_b",
+        "h_packed_grads")]
+
+
+# every entry point of include/castergvp.h: name -> (restype, argtypes)
+SIGNATURES = {
+    "cgvp_last_error": (C.c_char_p, []),
+    "cgvp_version": (C.c_int32, []),
+    "cgvp_sm_count": (C.c_int32, []),
+    "cgvp_gvp_packed_floats": (C.c_int64, [C.POINTER(GvpDesc)]),
+    "cgvp_pack_weights": (C.c_int32, [C.c_int32, C.POINTER(GvpDesc), C.POINTER(GvpWeights), C.POINTER(C.c_void_p),
+                                      C.c_void_p]),
+    "cgvp_unpack_grads": (C.c_int32, [C.c_int32, C.POINTER(GvpDesc), C.POINTER(C.c_void_p), C.POINTER(GvpGrads),
+                                      C.c_void_p]),
+    "cgvp_plan_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "cgvp_plan_build": (C.c_int32, [C.c_void_p, C.POINTER(Plan), C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_gather_message_input": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
+    "cgvp_segment_reduce": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p]),
+    "cgvp_conv_workspace_bytes": (C.c_int64, [C.POINTER(ConvDesc), C.c_int64, C.c_int64, C.c_int32]),
+    "cgvp_conv_fwd": (C.c_int32, [C.POINTER(ConvDesc), C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_conv_bwd": (C.c_int32, [C.POINTER(ConvDesc), C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_rows_workspace_bytes": (C.c_int64, [C.POINTER(RowDesc), C.c_int64, C.c_int32]),
+    "cgvp_rows_fwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_rows_bwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.POINTER(RowGradArgs), C.c_void_p,
+                                  C.c_int64, C.c_void_p]),
+    "cgvp_featurize_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "cgvp_featurize_count": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_featurize_fill": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+LAUNCHES = 0   # number of library calls that enqueue kernels (bench.py reports it)
+
+
+def lib():
+    """Load the shared object once.  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(or `make -C caster_dta_b200/csrc`). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    global LAUNCHES
+    LAUNCHES += 1
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().cgvp_last_error().decode()}")

@@ -1,0 +1,258 @@
+// Residue-graph featurizer for a batch of proteins: radius / kNN / proportional edge selection on C-alpha distances,
+// 16 Gaussian RBFs, 16 sin/cos sequence-offset encodings and the unit direction vector, written directly in COO
+// order (src ascending, dst ascending).  Replaces utils/create_protein_features.py:201-357 followed by
+// utils/create_graphs.py:6-62 without ever materialising the dense n x n x 35 fp64 array.
+//
+// Bit-exactness: the reference thresholds fp64 distances from scipy `pdist` on fp32 coordinates, i.e.
+// sqrt(((dx*dx) + dy*dy) + dz*dz) with every operation rounded separately.  The __d*_rn intrinsics below are never
+// contracted into FMAs, so the distance -- and therefore the edge set and edge_index -- is bit-identical.  The
+// direction vector follows numpy's fp32 arithmetic the same way.  RBF / sin / cos go through CUDA's fp64 libm
+// (<= 1-2 ulp in fp64) before the fp32 cast, so those features agree to <= 1 ulp(fp32).
+#include <cub/device/device_scan.cuh>
+
+#include "cgvp_common.cuh"
+
+#define FEAT_THREADS 128
+#define FEAT_WARPS (FEAT_THREADS / 32)
+
+// np.linspace(0., 20., 16) and np.exp(2*np.arange(8) * -(np.log(10000.0)/8)), printed with float.hex() from numpy 2.3
+__constant__ double c_rbf_mu[16] = {0x0.0p+0, 0x1.5555555555555p+0, 0x1.5555555555555p+1, 0x1.0000000000000p+2,
+                                    0x1.5555555555555p+2, 0x1.aaaaaaaaaaaaap+2, 0x1.0000000000000p+3, 0x1.2aaaaaaaaaaaap+3,
+                                    0x1.5555555555555p+3, 0x1.8000000000000p+3, 0x1.aaaaaaaaaaaaap+3, 0x1.d555555555555p+3,
+                                    0x1.0000000000000p+4, 0x1.1555555555555p+4, 0x1.2aaaaaaaaaaaap+4, 0x1.4000000000000p+4};
+__constant__ double c_pe_freq[8] = {0x1.0000000000000p+0, 0x1.9999999999998p-4, 0x1.47ae147ae1478p-7, 0x1.0624dd2f1a9f9p-10,
+                                    0x1.a36e2eb1c4326p-14, 0x1.4f8b588e368e5p-17, 0x1.0c6f7a0b5ed87p-20, 0x1.ad7f29abcaf44p-24};
+
+struct FeatK {
+    const float* ca;
+    const int64_t* ptr;
+    int64_t B, N;
+    double thresh;
+    int type, keep_self;
+    int* deg;
+    const int64_t* row_offsets;
+    int64_t *ei, E;
+    float *es, *ev;
+};
+
+__device__ __forceinline__ double ca_distance(const float* __restrict__ ca, int64_t i, int64_t j) {
+    const double dx = (double)ca[3 * i] - (double)ca[3 * j];
+    const double dy = (double)ca[3 * i + 1] - (double)ca[3 * j + 1];
+    const double dz = (double)ca[3 * i + 2] - (double)ca[3 * j + 2];
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+__device__ __forceinline__ int64_t find_protein(const int64_t* __restrict__ ptr, int64_t B, int64_t i) {
+    int64_t lo = 0, hi = B;   // largest b with ptr[b] <= i
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int knn_k(const FeatK& K, int64_t n) {
+    if (K.type == 2) return (int)ceil(K.thresh * (double)n);   // int(np.ceil(edge_thresh * n_residues))
+    return (int)K.thresh;                                      // int(edge_thresh)
+}
+
+// ---- phase 1: edges per source residue ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FEAT_THREADS) feat_count_kernel(const FeatK K) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < K.N; i += nwarps) {
+        const int64_t b = find_protein(K.ptr, K.B, i);
+        const int64_t lo = K.ptr[b], hi = K.ptr[b + 1], n = hi - lo;
+        int cnt;
+        if (K.type == 0) {
+            cnt = 0;
+            for (int64_t j0 = lo; j0 < hi; j0 += 32) {
+                const int64_t j = j0 + lane;
+                bool keep = false;
+                if (j < hi && (K.keep_self || j != i)) keep = ca_distance(K.ca, i, j) <= K.thresh;
+                cnt += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+        } else {
+            const int64_t valid = n - (K.keep_self ? 0 : 1);
+            const int64_t k = knn_k(K, n);
+            cnt = (int)(k < valid ? (k < 0 ? 0 : k) : valid);
+        }
+        if (lane == 0) K.deg[i] = cnt;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) K.deg[K.N] = 0;
+}
+
+// ---- phase 2: write edges and features -----------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_edge(const FeatK& K, int64_t e, int64_t i, int64_t j, double d, int lane) {
+    // 32 lanes = 32 scalar features of this edge: coalesced 128-byte row
+    float feat;
+    if (lane < 16) {
+        const double t = (d - c_rbf_mu[lane]) / 1.25;                       // (d - mu) / D_step            :237
+        feat = (float)exp(-(t * t));
+    } else {
+        const double ang = (double)(j - i) * c_pe_freq[lane & 7];            // (dst idx - src idx) * freq   :253,:382
+        feat = (float)(lane < 24 ? cos(ang) : sin(ang));
+    }
+    K.es[e * 32 + lane] = feat;
+    if (lane < 3) {
+        const float x = __fsub_rn(K.ca[3 * i], K.ca[3 * j]), y = __fsub_rn(K.ca[3 * i + 1], K.ca[3 * j + 1]),
+                    z = __fsub_rn(K.ca[3 * i + 2], K.ca[3 * j + 2]);                                    // :244
+        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        const float c = lane == 0 ? x : (lane == 1 ? y : z);
+        K.ev[e * 3 + lane] = nrm != 0.f ? __fdiv_rn(c, nrm) : 0.f;                                       // :360-365
+    }
+    if (lane == 0) { K.ei[e] = i; K.ei[K.E + e] = j; }
+}
+
+__device__ __forceinline__ void emit_chunk(const FeatK& K, unsigned mask, int64_t& e, int64_t i, int64_t j, double d, int lane) {
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t jj = __shfl_sync(0xffffffffu, j, src);
+        const double dd = __shfl_sync(0xffffffffu, d, src);
+        emit_edge(K, e, i, jj, dd, lane);
+        ++e;
+    }
+}
+
+__global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) {
+    __shared__ int hist[FEAT_WARPS][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < K.N; i += nwarps) {
+        const int64_t b = find_protein(K.ptr, K.B, i);
+        const int64_t lo = K.ptr[b], hi = K.ptr[b + 1], n = hi - lo;
+        int64_t e = K.row_offsets[i];
+        const int64_t e_end = K.row_offsets[i + 1];
+        if (e_end == e) continue;
+        if (K.type == 0) {
+            for (int64_t j0 = lo; j0 < hi; j0 += 32) {
+                const int64_t j = j0 + lane;
+                double d = 0.0;
+                bool keep = false;
+                if (j < hi && (K.keep_self || j != i)) { d = ca_distance(K.ca, i, j); keep = d <= K.thresh; }
+                emit_chunk(K, __ballot_sync(0xffffffffu, keep), e, i, j, d, lane);
+            }
+            continue;
+        }
+        // k nearest: radix-select the k-th smallest distance (fp64 bit pattern of a non-negative double is monotone),
+        // then keep d < T and the first (k - #{d < T}) ties in column order  (np.argsort(...)[:, :k], :319)
+        const int kk = (int)(e_end - e);
+        unsigned long long prefix = 0ull, pmask = 0ull;
+        int remaining = kk;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int q = lane; q < 256; q += 32) hist[wib][q] = 0;
+            __syncwarp();
+            for (int64_t j0 = lo; j0 < hi; j0 += 32) {
+                const int64_t j = j0 + lane;
+                if (j < hi && (K.keep_self || j != i)) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(ca_distance(K.ca, i, j));
+                    if ((key & pmask) == prefix) atomicAdd(&hist[wib][(int)((key >> shift) & 255ull)], 1);
+                }
+            }
+            __syncwarp();
+            // each lane owns 8 consecutive bins; warp-exclusive scan of the lane totals
+            int local[8], tot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { local[q] = hist[wib][lane * 8 + q]; tot += local[q]; }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int run = incl - tot, bin = -1, before = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (bin < 0 && run + local[q] >= remaining) { bin = lane * 8 + q; before = run; }
+                run += local[q];
+            }
+            const unsigned found = __ballot_sync(0xffffffffu, bin >= 0);
+            const int srcl = __ffs(found) - 1;
+            bin = __shfl_sync(0xffffffffu, bin, srcl);
+            before = __shfl_sync(0xffffffffu, before, srcl);
+            remaining -= before;
+            prefix |= (unsigned long long)bin << shift;
+            pmask |= 255ull << shift;
+            __syncwarp();
+        }
+        const double T = __longlong_as_double((long long)prefix);
+        int ties_left = remaining;             // how many entries equal to T are still to be taken
+        for (int64_t j0 = lo; j0 < hi; j0 += 32) {
+            const int64_t j = j0 + lane;
+            double d = 0.0;
+            bool lt = false, eq = false;
+            if (j < hi && (K.keep_self || j != i)) { d = ca_distance(K.ca, i, j); lt = d < T; eq = d == T; }
+            const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+            const bool take_eq = eq && __popc(eqm & ((1u << lane) - 1u)) < ties_left;
+            const unsigned tkm = __ballot_sync(0xffffffffu, take_eq);
+            ties_left -= __popc(tkm);
+            emit_chunk(K, __ballot_sync(0xffffffffu, lt) | tkm, e, i, j, d, lane);
+        }
+    }
+}
+
+static size_t scan_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int64_t*)nullptr, (int)n);
+    return b;
+}
+
+extern "C" int64_t cgvp_featurize_workspace_bytes(int64_t num_nodes, int64_t max_protein_len) {
+    if (num_nodes < 0 || num_nodes >= ((int64_t)1 << 31) - 1) return -1;
+    return align_up((num_nodes + 1) * 4, 256) + (int64_t)align_up((int64_t)scan_bytes(num_nodes + 1), 256) + 256;
+}
+
+static int feat_checks(const float* ca, const int64_t* ptr, int64_t B, int64_t N, int32_t type) {
+    CGVP_REQUIRE(B >= 0 && N >= 0 && N < ((int64_t)1 << 31) - 1, "featurize: bad sizes");
+    CGVP_REQUIRE(N == 0 || (ca && ptr && B > 0), "featurize: null input");
+    CGVP_REQUIRE(type >= 0 && type <= 2, "featurize: thresh_type must be 0 (dist), 1 (num) or 2 (prop)");
+    return 0;
+}
+
+extern "C" int32_t cgvp_featurize_count(const float* ca, const int64_t* ptr, int64_t num_proteins, int64_t num_nodes,
+                                        int64_t max_protein_len, double thresh, int32_t thresh_type,
+                                        int32_t keep_self_loops, int64_t* row_offsets, void* ws, int64_t ws_bytes,
+                                        cgvp_stream_t stream) {
+    if (feat_checks(ca, ptr, num_proteins, num_nodes, thresh_type)) return -1;
+    CGVP_REQUIRE(row_offsets, "featurize_count: null row_offsets");
+    const int64_t need = cgvp_featurize_workspace_bytes(num_nodes, max_protein_len);
+    CGVP_REQUIRE(ws && ws_bytes >= need, "featurize_count: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                 (long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    FeatK K;
+    memset(&K, 0, sizeof(K));
+    K.ca = ca; K.ptr = ptr; K.B = num_proteins; K.N = num_nodes; K.thresh = thresh; K.type = thresh_type;
+    K.keep_self = keep_self_loops != 0;
+    K.deg = reinterpret_cast<int*>(ws);
+    const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
+    int64_t blocks = cdiv64(num_nodes > 0 ? num_nodes : 1, FEAT_WARPS);
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    feat_count_kernel<<<(int)blocks, FEAT_THREADS, 0, st>>>(K);
+    CGVP_LAUNCH_CHECK("feat_count_kernel");
+    void* tmp = reinterpret_cast<char*>(ws) + align_up((num_nodes + 1) * 4, 256);
+    size_t tb = scan_bytes(num_nodes + 1);
+    CGVP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, (const int*)K.deg, row_offsets, (int)(num_nodes + 1), st));
+    return 0;
+}
+
+extern "C" int32_t cgvp_featurize_fill(const float* ca, const int64_t* ptr, int64_t num_proteins, int64_t num_nodes,
+                                       int64_t max_protein_len, double thresh, int32_t thresh_type,
+                                       int32_t keep_self_loops, const int64_t* row_offsets, int64_t* edge_index,
+                                       int64_t num_edges, float* edge_s, float* edge_v, void* ws, int64_t ws_bytes,
+                                       cgvp_stream_t stream) {
+    if (feat_checks(ca, ptr, num_proteins, num_nodes, thresh_type)) return -1;
+    CGVP_REQUIRE(num_edges >= 0, "featurize_fill: bad edge count");
+    if (num_edges == 0 || num_nodes == 0) return 0;
+    CGVP_REQUIRE(row_offsets && edge_index && edge_s && edge_v, "featurize_fill: null output");
+    FeatK K;
+    memset(&K, 0, sizeof(K));
+    K.ca = ca; K.ptr = ptr; K.B = num_proteins; K.N = num_nodes; K.thresh = thresh; K.type = thresh_type;
+    K.keep_self = keep_self_loops != 0;
+    K.row_offsets = row_offsets; K.ei = edge_index; K.E = num_edges; K.es = edge_s; K.ev = edge_v;
+    const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
+    int64_t blocks = cdiv64(num_nodes, FEAT_WARPS);
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    feat_fill_kernel<<<(int)blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(K);
+    CGVP_LAUNCH_CHECK("feat_fill_kernel");
+    return 0;
+}

@@ -1,0 +1,218 @@
+// Graph plan (dst-sorted and src-sorted CSR views of edge_index) and the two stand-alone HBM-bound primitives:
+// message-input gather and deterministic segmented reduction.  Replaces the index handling of PyG
+// MessagePassing.propagate as used by GVPConv (models/gvp_layers.py:298-300).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cgvp_common.cuh"
+
+// ---- plan ---------------------------------------------------------------------------------------------------------
+__global__ void plan_prepare_kernel(const int64_t* __restrict__ edge_index, int64_t E, int* __restrict__ key_dst,
+                                    int* __restrict__ iota) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    key_dst[e] = (int)edge_index[E + e];
+    iota[e] = (int)e;
+}
+
+__global__ void plan_gather_src_kernel(const int64_t* __restrict__ edge_index, int64_t E, const int* __restrict__ perm,
+                                       int* __restrict__ src_sorted) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    src_sorted[p] = (int)edge_index[perm[p]];
+}
+
+// rowptr[n] = first position whose (sorted) key is >= n
+__global__ void plan_rowptr_kernel(const int* __restrict__ sorted_keys, int64_t E, int64_t N, int* __restrict__ rowptr) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > N) return;
+    int64_t lo = 0, hi = E;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < n) lo = mid + 1; else hi = mid;
+    }
+    rowptr[n] = (int)lo;
+}
+
+static int bits_for(int64_t n) {
+    int b = 1;
+    while (((int64_t)1 << b) < n && b < 31) ++b;
+    return b;
+}
+
+static size_t cub_sort_bytes(int64_t E, int64_t N) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, (int)E, 0, bits_for(N));
+    return bytes;
+}
+
+extern "C" int64_t cgvp_plan_workspace_bytes(int64_t num_edges, int64_t num_nodes) {
+    if (num_edges < 0 || num_nodes < 0 || num_edges >= ((int64_t)1 << 31) || num_nodes >= ((int64_t)1 << 31)) return -1;
+    const int64_t e4 = align_up(num_edges * 4, 256);
+    return 3 * e4 + (int64_t)align_up((int64_t)cub_sort_bytes(num_edges, num_nodes), 256) + 256;
+}
+
+extern "C" int32_t cgvp_plan_build(const int64_t* edge_index, const CgvpPlan* plan, void* ws, int64_t ws_bytes,
+                                   cgvp_stream_t stream) {
+    CGVP_REQUIRE(plan, "plan_build: null plan");
+    const int64_t E = plan->num_edges, N = plan->num_nodes;
+    CGVP_REQUIRE(E >= 0 && N >= 0 && E < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "plan_build: sizes out of range");
+    CGVP_REQUIRE(plan->rowptr && plan->srowptr, "plan_build: null rowptr");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = 256;
+    if (E > 0) {
+        CGVP_REQUIRE(edge_index && plan->perm && plan->src && plan->dst && plan->sperm, "plan_build: null buffer");
+        const int64_t need = cgvp_plan_workspace_bytes(E, N);
+        CGVP_REQUIRE(ws && ws_bytes >= need, "plan_build: workspace too small (%lld < %lld)", (long long)ws_bytes,
+                     (long long)need);
+        const int64_t e4 = align_up(E * 4, 256);
+        char* base = reinterpret_cast<char*>(ws);
+        int* key = reinterpret_cast<int*>(base);
+        int* iota = reinterpret_cast<int*>(base + e4);
+        int* skey = reinterpret_cast<int*>(base + 2 * e4);
+        void* cub_tmp = base + 3 * e4;
+        size_t cub_bytes = cub_sort_bytes(E, N);
+        const int grid = (int)cdiv64(E, T);
+        plan_prepare_kernel<<<grid, T, 0, st>>>(edge_index, E, key, iota);
+        CGVP_LAUNCH_CHECK("plan_prepare_kernel");
+        // stable LSD radix sort by target: ties keep the original edge order, so the summation order is reproducible
+        CGVP_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const int*)key, plan->dst, (const int*)iota,
+                                                  plan->perm, (int)E, 0, bits_for(N), st));
+        plan_gather_src_kernel<<<grid, T, 0, st>>>(edge_index, E, plan->perm, plan->src);
+        CGVP_LAUNCH_CHECK("plan_gather_src_kernel");
+        // second view: dst-sorted positions ordered by source
+        CGVP_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const int*)plan->src, skey, (const int*)iota,
+                                                  plan->sperm, (int)E, 0, bits_for(N), st));
+        plan_rowptr_kernel<<<(int)cdiv64(N + 1, T), T, 0, st>>>(plan->dst, E, N, plan->rowptr);
+        CGVP_LAUNCH_CHECK("plan_rowptr_kernel");
+        plan_rowptr_kernel<<<(int)cdiv64(N + 1, T), T, 0, st>>>(skey, E, N, plan->srowptr);
+        CGVP_LAUNCH_CHECK("plan_rowptr_kernel");
+    } else {
+        CGVP_CUDA(cudaMemsetAsync(plan->rowptr, 0, (size_t)(N + 1) * 4, st));
+        CGVP_CUDA(cudaMemsetAsync(plan->srowptr, 0, (size_t)(N + 1) * 4, st));
+    }
+    return 0;
+}
+
+// ---- gather of the message input (gvp_layers.py:303-306) ----------------------------------------------------------
+// One thread per output float4 (scalars) / float (vectors); writes are fully coalesced, reads are row segments.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) gather_scalar_kernel(const int64_t* __restrict__ ei, int64_t E, int ns, int es,
+                                                            const float* __restrict__ s, const float* __restrict__ e_s,
+                                                            float* __restrict__ ms) {
+    constexpr int V = VEC4 ? 4 : 1;
+    const int w = (2 * ns + es) / V, nsv = ns / V, esv = es / V;
+    const int64_t total = E * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / w;
+        const int c = (int)(i - e * w);
+        const float* src;
+        if (c < nsv) src = s + ei[e] * ns + c * V;
+        else if (c < nsv + esv) src = e_s + e * es + (c - nsv) * V;
+        else src = s + ei[E + e] * ns + (c - nsv - esv) * V;
+        if (VEC4) reinterpret_cast<float4*>(ms)[i] = __ldg(reinterpret_cast<const float4*>(src));
+        else ms[i] = __ldg(src);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_vector_kernel(const int64_t* __restrict__ ei, int64_t E, int nv, int ev,
+                                                            const float* __restrict__ v, const float* __restrict__ e_v,
+                                                            float* __restrict__ mv) {
+    const int w = 3 * (2 * nv + ev), nvw = 3 * nv, evw = 3 * ev;
+    const int64_t total = E * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / w;
+        const int c = (int)(i - e * w);
+        float val;
+        if (c < nvw) val = __ldg(v + ei[e] * nvw + c);
+        else if (c < nvw + evw) val = __ldg(e_v + e * evw + (c - nvw));
+        else val = __ldg(v + ei[E + e] * nvw + (c - nvw - evw));
+        mv[i] = val;
+    }
+}
+
+extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t num_edges, int32_t ns, int32_t nv,
+                                             int32_t es, int32_t ev, const float* s, const float* v, const float* e_s,
+                                             const float* e_v, float* ms, float* mv, cgvp_stream_t stream) {
+    CGVP_REQUIRE(num_edges >= 0 && ns >= 0 && nv >= 0 && es >= 0 && ev >= 0, "gather: bad sizes");
+    if (num_edges == 0) return 0;
+    CGVP_REQUIRE(edge_index, "gather: null edge_index");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
+    if (2 * ns + es > 0) {
+        CGVP_REQUIRE(ms && (ns == 0 || s) && (es == 0 || e_s), "gather: null scalar buffer");
+        const bool vec = ns % 4 == 0 && es % 4 == 0 && (((uintptr_t)s | (uintptr_t)e_s | (uintptr_t)ms) & 15) == 0;
+        const int64_t total = num_edges * ((2 * ns + es) / (vec ? 4 : 1));
+        const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
+        if (vec) gather_scalar_kernel<true><<<grid, 256, 0, st>>>(edge_index, num_edges, ns, es, s, e_s, ms);
+        else gather_scalar_kernel<false><<<grid, 256, 0, st>>>(edge_index, num_edges, ns, es, s, e_s, ms);
+        CGVP_LAUNCH_CHECK("gather_scalar_kernel");
+    }
+    if (2 * nv + ev > 0) {
+        CGVP_REQUIRE(mv && (nv == 0 || v) && (ev == 0 || e_v), "gather: null vector buffer");
+        const int64_t total = num_edges * 3 * (2 * nv + ev);
+        const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
+        gather_vector_kernel<<<grid, 256, 0, st>>>(edge_index, num_edges, nv, ev, v, e_v, mv);
+        CGVP_LAUNCH_CHECK("gather_vector_kernel");
+    }
+    return 0;
+}
+
+// ---- deterministic segmented reduction -------------------------------------------------------------------------------
+// out[n][c] (+)= scale(n) * sum_{p in [rowptr[n], rowptr[n+1])} rows[index[p]][c], summed in position order.
+// The output may be split into two tensors (widths wa | wb) so merged message rows can land in (s, V) pairs.
+template <int V>
+__global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __restrict__ rows, int width,
+                                                             const int* __restrict__ rowptr, const int* __restrict__ index,
+                                                             int64_t N, int aggr, int beta, float* __restrict__ out_a,
+                                                             int wa, float* __restrict__ out_b, int wb) {
+    const int wv = width / V;
+    const int64_t total = N * wv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / wv;
+        const int c = (int)(i - n * wv) * V;
+        const int p0 = rowptr[n], p1 = rowptr[n + 1];
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        for (int p = p0; p < p1; ++p) {
+            const int64_t r = index ? index[p] : p;
+            if (V == 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(rows + r * width + c));
+                acc[0] += x.x; acc[1 % V] += x.y; acc[2 % V] += x.z; acc[3 % V] += x.w;
+            } else {
+                acc[0] += __ldg(rows + r * width + c);
+            }
+        }
+        const float scale = (aggr == CGVP_AGGR_MEAN) ? 1.f / (float)max(p1 - p0, 1) : 1.f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int cc = c + k;
+            float* dst = cc < wa ? out_a + n * wa + cc : out_b + n * wb + (cc - wa);
+            const float val = acc[k] * scale;
+            *dst = beta ? *dst + val : val;
+        }
+    }
+}
+
+int cgvp_segment_reduce_split(const float* rows, int width, const int* rowptr, const int* index, int64_t N, int aggr,
+                              int beta, float* out_a, int wa, float* out_b, int wb, cudaStream_t st) {
+    if (N == 0 || width == 0) return 0;
+    const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
+    const bool vec = width % 4 == 0 && ((uintptr_t)rows & 15) == 0;
+    const int64_t total = N * (width / (vec ? 4 : 1));
+    const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
+    if (vec) segment_reduce_kernel<4><<<grid, 256, 0, st>>>(rows, width, rowptr, index, N, aggr, beta, out_a, wa, out_b, wb);
+    else segment_reduce_kernel<1><<<grid, 256, 0, st>>>(rows, width, rowptr, index, N, aggr, beta, out_a, wa, out_b, wb);
+    CGVP_LAUNCH_CHECK("segment_reduce_kernel");
+    return 0;
+}
+
+extern "C" int32_t cgvp_segment_reduce(const float* rows, int32_t width, const int32_t* rowptr, const int32_t* index,
+                                       int64_t num_nodes, int32_t aggr, int32_t beta, float* out, cgvp_stream_t stream) {
+    CGVP_REQUIRE(width >= 0 && num_nodes >= 0, "segment_reduce: bad sizes");
+    if (num_nodes == 0 || width == 0) return 0;
+    CGVP_REQUIRE(rows && rowptr && out, "segment_reduce: null buffer");
+    return cgvp_segment_reduce_split(rows, width, rowptr, index, num_nodes, aggr, beta, out, width, nullptr, 0,
+                                     (cudaStream_t)stream);
+}

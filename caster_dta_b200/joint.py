@@ -1,0 +1,262 @@
+"""CASTER-DTA joint model around the accelerated protein encoder.
+
+Only `protein_gnn` (the GVP stack) runs on the custom kernels.  The molecule GINE encoder, the cross-attention
+block and the MLP head are small dense / scalar graph ops that stay stock PyTorch ("host code stays PyTorch");
+they are written here without torch_geometric so that `JointGNN(**model_kwargs.json)` builds and the shipped
+checkpoint loads with strict=True:
+
+    JointGNN                <- models/joint_gnn.py:15-288
+    CrossAttentionModule    <- models/joint_gnn.py:321-408
+    GINE molecule encoder   <- models/molecule_gnn.py:208-280 (+ PyG GINEConv / MLP semantics)
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .encoder import SelectableProteinModelWrapper
+
+
+def _activation(name):
+    table = {"relu": nn.ReLU, "leaky_relu": lambda: nn.LeakyReLU(0.01), "tanh": nn.Tanh, "sigmoid": nn.Sigmoid,
+             "gelu": nn.GELU, "elu": nn.ELU, "selu": nn.SELU, "silu": nn.SiLU, "swish": nn.SiLU, "none": nn.Identity}
+    if isinstance(name, nn.Module):
+        return name
+    return table[name.lower()]()
+
+
+class _MLP(nn.Module):
+    """Two-layer perceptron with the parameter names of PyG's `MLP` (`lins.0`, `lins.1`), plain last layer."""
+
+    def __init__(self, dims, act):
+        super().__init__()
+        self.lins = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        self.act = act
+
+    def forward(self, x):
+        for lin in self.lins[:-1]:
+            x = self.act(lin(x))
+        return self.lins[-1](x)
+
+
+class GINEConv(nn.Module):
+    """out_i = nn((1 + eps) x_i + sum_j relu(x_j + lin(e_ji)))  (PyG GINEConv)."""
+
+    def __init__(self, mlp, edge_dim, train_eps=True):
+        super().__init__()
+        self.nn = mlp
+        if train_eps:
+            self.eps = nn.Parameter(torch.zeros(1))
+        else:
+            self.register_buffer("eps", torch.zeros(1))
+        self.lin = nn.Linear(edge_dim, mlp.lins[0].in_features)
+
+    def forward(self, x, edge_index, edge_attr):
+        msg = F.relu(x.index_select(0, edge_index[0]) + self.lin(edge_attr))
+        agg = torch.zeros_like(x).index_add_(0, edge_index[1], msg)
+        return self.nn(agg + (1 + self.eps) * x)
+
+
+class HomoMoleculeGNN_GINE(nn.Module):
+    def __init__(self, in_channels, edge_dim, num_ntypes, num_etypes, ntype_emb_dim, etype_emb_dim, num_convs=1,
+                 hidden_channels=None, out_channels=8, dropout_rate=0.2, activation="relu", aggr="sum",
+                 gin_trainable_eps=True, **unused):
+        super().__init__()
+        if ntype_emb_dim is not None or etype_emb_dim is not None:
+            raise NotImplementedError("learned type embeddings are not used by the shipped configuration")
+        if aggr not in ("sum", "add"):
+            raise NotImplementedError("GINE stand-in implements sum aggregation")
+        self.num_ntypes, self.num_etypes, self.out_channels = num_ntypes, num_etypes, out_channels
+        hidden = out_channels if hidden_channels is None else hidden_channels
+        self.activation = _activation(activation)
+        self.dropout = nn.Dropout(dropout_rate)
+        dims = [in_channels + num_ntypes] + [hidden] * (num_convs - 1) + [out_channels]
+        self.conv_list = nn.ModuleList(
+            GINEConv(_MLP([dims[i], dims[i + 1], dims[i + 1]], self.activation), edge_dim + num_etypes, gin_trainable_eps)
+            for i in range(num_convs))
+
+    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
+        x = torch.cat([F.one_hot(ntypes, self.num_ntypes).to(x.dtype), x], -1)
+        e = torch.cat([F.one_hot(etypes, self.num_etypes).to(x.dtype), eattr], -1)
+        for conv in self.conv_list[:-1]:
+            x = self.dropout(self.activation(conv(x, edge_index, e)))
+        return self.activation(self.conv_list[-1](x, edge_index, e))
+
+
+class SelectableMoleculeModelWrapper(nn.Module):
+    def __init__(self, base_conv, **kwargs):
+        super().__init__()
+        if base_conv.lower() != "gine":
+            raise NotImplementedError(f"molecule encoder {base_conv!r}: only the shipped 'gine' configuration is provided")
+        self.base_conv = base_conv.lower()
+        self.gnn_model = HomoMoleculeGNN_GINE(**kwargs)
+
+    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
+        return self.gnn_model(x, edge_index, ntypes, etypes, eattr=eattr, batch=batch)
+
+    @property
+    def out_channels(self):
+        return self.gnn_model.out_channels
+
+
+def to_dense_batch(x, batch, num_graphs=None, max_nodes=None):
+    """[total, D] + graph id per row -> ([B, max, D], mask [B, max]).  Pass num_graphs / max_nodes to avoid the
+    device->host syncs of computing them."""
+    if batch is None:
+        return x.unsqueeze(0), torch.ones(1, x.shape[0], dtype=torch.bool, device=x.device)
+    b = int(batch[-1]) + 1 if num_graphs is None else int(num_graphs)
+    counts = torch.bincount(batch, minlength=b)
+    start = torch.cumsum(counts, 0) - counts
+    m = int(counts.max()) if max_nodes is None else int(max_nodes)
+    pos = torch.arange(x.shape[0], device=x.device) - start[batch]
+    out = x.new_zeros((b, m, x.shape[1]))
+    out[batch, pos] = x
+    mask = torch.zeros(b, m, dtype=torch.bool, device=x.device)
+    mask[batch, pos] = True
+    return out, mask
+
+
+class CrossAttentionModule(nn.Module):
+    def __init__(self, embed_dim_1, embed_dim_2, n_attention_heads, attn_dropout, include_residual_stream=True,
+                 dim_feedforward_scale=2, feedforward_dropout=0.2):
+        super().__init__()
+        self.include_residual_stream = include_residual_stream
+        self.preattn_norm1, self.preattn_norm2 = nn.LayerNorm(embed_dim_1), nn.LayerNorm(embed_dim_2)
+        self.embed1_to_2 = nn.MultiheadAttention(embed_dim_1, n_attention_heads, dropout=attn_dropout, kdim=embed_dim_2,
+                                                 vdim=embed_dim_2, batch_first=True)
+        self.embed2_to_1 = nn.MultiheadAttention(embed_dim_2, n_attention_heads, dropout=attn_dropout, kdim=embed_dim_1,
+                                                 vdim=embed_dim_1, batch_first=True)
+        self.ff_norm1, self.ff_norm2 = nn.LayerNorm(embed_dim_1), nn.LayerNorm(embed_dim_2)
+        self.ff_dropout = nn.Dropout(feedforward_dropout)
+        if include_residual_stream:
+            def ff(d):
+                return nn.Sequential(nn.Linear(d, d * dim_feedforward_scale), nn.ReLU(), nn.Dropout(feedforward_dropout),
+                                     nn.Linear(d * dim_feedforward_scale, d))
+            self.ff1, self.ff2 = ff(embed_dim_1), ff(embed_dim_2)
+
+    def forward(self, e1, e2, mask1, mask2, return_weights=True):
+        n1, n2 = self.preattn_norm1(e1), self.preattn_norm2(e2)
+        a1, w1 = self.embed1_to_2(n1, n2, n2, key_padding_mask=~mask2, need_weights=return_weights)
+        a2, w2 = self.embed2_to_1(n2, n1, n1, key_padding_mask=~mask1, need_weights=return_weights)
+        if self.include_residual_stream:
+            e1 = e1 + self.ff_dropout(a1)
+            e1 = e1 + self.ff_dropout(self.ff1(self.ff_norm1(e1)))
+            e2 = e2 + self.ff_dropout(a2)
+            e2 = e2 + self.ff_dropout(self.ff2(self.ff_norm2(e2)))
+        else:
+            e1, e2 = a1, a2
+        return e1, e2, (w1, w2)
+
+
+class StackedCrossAttentionModule(nn.Module):
+    def __init__(self, make_layer, num_layers):
+        super().__init__()
+        self.cross_attn_layers = nn.ModuleList(make_layer() for _ in range(num_layers))
+
+    def forward(self, e1, e2, mask1, mask2, return_weights=True):
+        weights = []
+        for layer in self.cross_attn_layers:
+            e1, e2, w = layer(e1, e2, mask1, mask2, return_weights)
+            weights.append(w)
+        return e1, e2, weights
+
+
+def _lin_stack(depth, in_dim, scale=2, norm=None):
+    lins, norms, d = [], [], in_dim
+    for _ in range(depth):
+        o = int(d * scale)
+        lins.append(nn.Linear(d, o))
+        norms.append(nn.LayerNorm(o) if norm == "layer" else nn.Identity())
+        d = o
+    return nn.ModuleList(lins), nn.ModuleList(norms), d
+
+
+class JointGNN(nn.Module):
+    """Same constructor and `forward` / `forward_with_graphs` as `models/joint_gnn.py:15-170`; returns
+    `(affinity [B,1], attention weights)`.  Set `return_attention=False` to let the attention use the fused SDPA path."""
+
+    def __init__(self, protein_gnn_kwargs, molecule_gnn_kwargs, residue_lin_depth, atom_lin_depth, n_attention_heads,
+                 attention_dropout, protein_lin_depth, molecule_lin_depth, pairwise_embedding_dim, out_lin_depth,
+                 out_lin_factor=0.5, out_lin_norm_type=None, activation="relu", dropout=0.0, element_pooling="mean",
+                 include_residual_stream=True, residual_dim_ff_scale=2, num_cross_attn_layers=1,
+                 include_post_pool_layernorm=False):
+        super().__init__()
+        if out_lin_norm_type == "batch":
+            raise NotImplementedError("batch norm in the output stack needs torch_geometric")
+        self.element_pooling = element_pooling
+        self.num_cross_attn_layers = num_cross_attn_layers
+        self.include_post_pool_layernorm = include_post_pool_layernorm
+        self.return_attention = True
+        self.activation = _activation(activation)
+        self.dropout = nn.Dropout(dropout)
+        self.protein_gnn = SelectableProteinModelWrapper(**protein_gnn_kwargs)
+        self.molecule_gnn = SelectableMoleculeModelWrapper(**molecule_gnn_kwargs)
+        p_out = self.protein_gnn.out_channels
+        p_out = p_out[0] if isinstance(p_out, tuple) else p_out
+        m_out = self.molecule_gnn.out_channels
+        self.residue_lins, self.residue_norms, r_dim = _lin_stack(residue_lin_depth, p_out)
+        self.atom_lins, self.atom_norms, a_dim = _lin_stack(atom_lin_depth, m_out)
+        if num_cross_attn_layers > 0:
+            self.cross_attn_module = StackedCrossAttentionModule(
+                lambda: CrossAttentionModule(r_dim, a_dim, n_attention_heads, attention_dropout, include_residual_stream,
+                                             residual_dim_ff_scale, dropout), num_cross_attn_layers)
+        else:
+            self.cross_attn_module = None
+        if include_post_pool_layernorm:
+            self.protein_post_pool_norm, self.molecule_post_pool_norm = nn.LayerNorm(r_dim), nn.LayerNorm(a_dim)
+        self.protein_lins, self.protein_norms, pd = _lin_stack(protein_lin_depth, r_dim)
+        self.molecule_lins, self.molecule_norms, md = _lin_stack(molecule_lin_depth, a_dim)
+        self.pm_embed_lin = nn.Linear(pd + md, pairwise_embedding_dim)
+        self.out_fc_layers, self.out_fc_norms, od = _lin_stack(out_lin_depth, pairwise_embedding_dim, out_lin_factor,
+                                                               out_lin_norm_type)
+        self.output_layer = nn.Linear(od, 1)
+
+    @staticmethod
+    def _graphs_to_dicts(protein_graph, molecule_graph):
+        def as_dict(g):
+            return {"x": g.x, "edge_index": g.edge_index, "ntypes": g.node_type, "etypes": g.edge_type,
+                    "eattr": g.edge_attr, "batch": g.batch}
+        return as_dict(protein_graph), as_dict(molecule_graph)
+
+    def forward_with_graphs(self, protein_graph, molecule_graph):
+        return self.forward(*self._graphs_to_dicts(protein_graph, molecule_graph))
+
+    def _stack(self, x, lins, norms):
+        for lin, norm in zip(lins, norms):
+            x = self.dropout(self.activation(norm(lin(x))))
+        return x
+
+    def _pool(self, x, mask):
+        if self.element_pooling == "mean":
+            return (x * mask.unsqueeze(-1)).sum(1) / mask.sum(1, keepdim=True)
+        if self.element_pooling == "sum":
+            return (x * mask.unsqueeze(-1)).sum(1)
+        if self.element_pooling == "max":
+            return (x - (~mask).unsqueeze(-1) * 1.0e10).max(1).values
+        raise ValueError(self.element_pooling)
+
+    def forward(self, protein_graph_data={}, molecule_graph_data={}):
+        pg, mg = dict(protein_graph_data), dict(molecule_graph_data)
+        hints_p = {k: pg.pop(k, None) for k in ("num_graphs", "max_nodes")}
+        hints_m = {k: mg.pop(k, None) for k in ("num_graphs", "max_nodes")}
+        res = self._stack(self.protein_gnn(**pg), self.residue_lins, self.residue_norms)
+        atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
+        res, rmask = to_dense_batch(res, pg.get("batch"), **hints_p)
+        atm, amask = to_dense_batch(atm, mg.get("batch"), **hints_m)
+        weights = None
+        if self.cross_attn_module is not None:
+            res, atm, weights = self.cross_attn_module(res, atm, rmask, amask, self.return_attention)
+        pe, me = self._pool(res, rmask), self._pool(atm, amask)
+        if self.include_post_pool_layernorm:
+            pe, me = self.protein_post_pool_norm(pe), self.molecule_post_pool_norm(me)
+        pe = self._stack(self.dropout(self.activation(pe)), self.protein_lins, self.protein_norms)
+        me = self._stack(self.dropout(self.activation(me)), self.molecule_lins, self.molecule_norms)
+        x = self.dropout(self.activation(self.pm_embed_lin(torch.cat([pe, me], -1))))
+        x = self._stack(x, self.out_fc_layers, self.out_fc_norms)
+        return self.output_layer(x), weights
+
+
+def load_state_dict_from_checkpoint(model, state_dict, strict=True):
+    """`inference/inference_utils.py:54-67`: checkpoints are saved from the torch.compile'd module, so every key
+    carries an `_orig_mod.` prefix."""
+    clean = {(k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k): v for k, v in state_dict.items()}
+    return model.load_state_dict(clean, strict=strict)

@@ -1,0 +1,365 @@
+"""Torch-facing wrappers of the C ABI: graph plans, weight packing and the two autograd Functions.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic of the GVP hot path
+happens in `libcastergvp.so`.  Every call is enqueued on the current CUDA stream.
+"""
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("castergvp ops need CUDA tensors (there is no CPU fallback)")
+    return t.detach().contiguous().float()
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256) + 256, dtype=torch.uint8, device=device)
+
+
+def _aligned_ptr(ws, align=256):
+    p = ws.data_ptr()
+    return C.c_void_p((p + align - 1) // align * align), ws.numel() - align
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class GvpSpec:
+    """Static description of one GVP (`models/gvp_layers.py:123-140`)."""
+    __slots__ = ("si", "vi", "so", "vo", "h", "sact", "vact", "gate")
+
+    def __init__(self, si, vi, so, vo, h, sact, vact, gate):
+        self.si, self.vi, self.so, self.vo = int(si), int(vi), int(so), int(vo)
+        self.h = int(h) if vi else 0
+        self.sact, self.vact, self.gate = int(sact), int(vact), int(bool(gate))
+
+    def desc(self):
+        return _lib.GvpDesc(self.si, self.vi, self.so, self.vo, max(self.h, 0), self.sact, self.vact, self.gate)
+
+    def key(self):
+        return (self.si, self.vi, self.so, self.vo, self.h, self.sact, self.vact, self.gate)
+
+    @property
+    def has_wh(self):
+        return self.vi > 0
+
+    @property
+    def has_wv(self):
+        return self.vi > 0 and self.vo > 0
+
+    @property
+    def has_gate(self):
+        return self.has_wv and self.gate == 1
+
+    def packed_floats(self):
+        d = self.desc()
+        return int(lib().cgvp_gvp_packed_floats(C.byref(d)))
+
+
+WEIGHTS_PER_GVP = 6   # wh, ws.weight, ws.bias, wv, wsv.weight, wsv.bias (None where absent)
+
+
+def pack_weights(specs, weights, device):
+    """PyTorch-layout parameters -> one packed arena.  Returns (arena, [block offsets in floats])."""
+    offs, total = [], 0
+    for sp in specs:
+        offs.append(total)
+        total += (sp.packed_floats() + 3) // 4 * 4
+    arena = torch.empty(max(total, 4), dtype=torch.float32, device=device)
+    n = len(specs)
+    if n == 0:
+        return arena, offs
+    descs = (_lib.GvpDesc * n)(*[sp.desc() for sp in specs])
+    wts = (_lib.GvpWeights * n)()
+    keep = []
+    for i in range(n):
+        w = [_f32(t) for t in weights[WEIGHTS_PER_GVP * i: WEIGHTS_PER_GVP * (i + 1)]]
+        keep.append(w)
+        for name, t in zip(("wh", "ws", "bs", "wv", "wsv", "bg"), w):
+            setattr(wts[i], name, None if t is None else t.data_ptr())
+    blocks = (C.c_void_p * n)(*[arena.data_ptr() + 4 * o for o in offs])
+    check(lib().cgvp_pack_weights(n, descs, wts, blocks, _stream()), "cgvp_pack_weights")
+    return arena, offs
+
+
+def unpack_grads(specs, packed_grads, offs, weights):
+    """Packed gradient blocks -> list of PyTorch-layout gradient tensors (None where the weight is None)."""
+    n = len(specs)
+    out = []
+    if n == 0:
+        return out
+    descs = (_lib.GvpDesc * n)(*[sp.desc() for sp in specs])
+    gr = (_lib.GvpGrads * n)()
+    for i in range(n):
+        for j, name in enumerate(("wh", "ws", "bs", "wv", "wsv", "bg")):
+            w = weights[WEIGHTS_PER_GVP * i + j]
+            g = None if w is None else torch.empty(w.shape, dtype=torch.float32, device=packed_grads.device)
+            out.append(g)
+            setattr(gr[i], name, None if g is None else g.data_ptr())
+    blocks = (C.c_void_p * n)(*[packed_grads.data_ptr() + 4 * o for o in offs])
+    check(lib().cgvp_unpack_grads(n, descs, blocks, gr, _stream()), "cgvp_unpack_grads")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class GraphPlan:
+    """dst-sorted / src-sorted CSR views of an edge_index (see `CgvpPlan` in castergvp.h)."""
+
+    def __init__(self, edge_index, num_nodes):
+        if not edge_index.is_cuda:
+            raise RuntimeError("GraphPlan needs a CUDA edge_index (there is no CPU fallback)")
+        ei = edge_index.detach().contiguous().long()
+        dev = ei.device
+        self.E, self.N = int(ei.shape[1]), int(num_nodes)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.perm = torch.empty(self.E, **i32)
+        self.src = torch.empty(self.E, **i32)
+        self.dst = torch.empty(self.E, **i32)
+        self.rowptr = torch.empty(self.N + 1, **i32)
+        self.sperm = torch.empty(self.E, **i32)
+        self.srowptr = torch.empty(self.N + 1, **i32)
+        nbytes = lib().cgvp_plan_workspace_bytes(self.E, self.N)
+        if nbytes < 0:
+            raise RuntimeError("graph too large for int32 indexing")
+        ws = _workspace(nbytes, dev)
+        wp, wn = _aligned_ptr(ws)
+        self.c = _lib.Plan(self.E, self.N, self.perm.data_ptr(), self.src.data_ptr(), self.dst.data_ptr(),
+                           self.rowptr.data_ptr(), self.sperm.data_ptr(), self.srowptr.data_ptr())
+        check(lib().cgvp_plan_build(_ptr(ei), C.byref(self.c), wp, wn, _stream()), "cgvp_plan_build")
+        self._keep = ei
+
+
+_plan_cache = {}
+
+
+def get_plan(edge_index, num_nodes):
+    """Plan cached per edge_index tensor (same storage, shape and version -> same plan), so the two conv layers of
+    a model and repeated steps over the same batch sort the edges once."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), edge_index.device.index)
+    hit = _plan_cache.get(key)
+    if hit is not None and hit[0]() is not None:
+        return hit[1]
+    if len(_plan_cache) > 64:
+        _plan_cache.clear()
+    plan = GraphPlan(edge_index, num_nodes)
+    _plan_cache[key] = (weakref.ref(edge_index), plan)
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class RowProgram:
+    """Static description of a fused row program (`CgvpRowDesc`)."""
+
+    def __init__(self, in_s, in_v, gvps, onehot=0, residual_in=False, pre_norm=False, post_residual=False,
+                 post_norm=False):
+        assert len(gvps) <= _lib.MAX_CHAIN
+        self.in_s, self.in_v, self.gvps = int(in_s), int(in_v), list(gvps)
+        self.onehot, self.residual_in, self.pre_norm = int(onehot), bool(residual_in), bool(pre_norm)
+        self.post_residual, self.post_norm = bool(post_residual), bool(post_norm)
+        if gvps:
+            self.out_s, self.out_v = gvps[-1].so, gvps[-1].vo
+        else:
+            self.out_s, self.out_v = self.onehot + self.in_s, self.in_v
+        d = _lib.RowDesc()
+        d.in_s, d.in_v, d.onehot, d.has_residual_in = self.in_s, self.in_v, self.onehot, int(self.residual_in)
+        d.pre_norm, d.n_gvp, d.post_residual, d.post_norm = int(self.pre_norm), len(gvps), int(self.post_residual), int(self.post_norm)
+        for i, g in enumerate(gvps):
+            d.gvp[i] = g.desc()
+        self.desc = d
+
+
+def _row_args(prog, rows, t, arena, offs):
+    a = _lib.RowArgs()
+    a.rows = rows
+    for name in ("in_s", "in_v", "types", "in_index", "h_s", "h_v", "mask0_s", "mask0_v", "mask1_s", "mask1_v",
+                 "ln0_w", "ln0_b", "ln1_w", "ln1_b", "out_s", "out_v"):
+        v = t.get(name)
+        setattr(a, name, None if v is None else v.data_ptr())
+    blocks = (C.c_void_p * max(len(offs), 1))(*[arena.data_ptr() + 4 * o for o in offs])
+    a.h_packed = C.addressof(blocks)
+    return a, blocks
+
+
+class RowsFunction(torch.autograd.Function):
+    """autograd wrapper of cgvp_rows_fwd / cgvp_rows_bwd."""
+
+    @staticmethod
+    def forward(ctx, prog, in_s, in_v, types, in_index, h_s, h_v, m0s, m0v, m1s, m1v, ln0_w, ln0_b, ln1_w, ln1_b,
+                *weights):
+        dev = in_s.device
+        t = dict(in_s=_f32(in_s), in_v=_f32(in_v) if prog.in_v else None,
+                 types=None if types is None else types.contiguous().long(),
+                 in_index=None if in_index is None else in_index.contiguous().int(),
+                 h_s=_f32(h_s), h_v=_f32(h_v) if prog.in_v else None,
+                 mask0_s=_f32(m0s), mask0_v=_f32(m0v), mask1_s=_f32(m1s), mask1_v=_f32(m1v),
+                 ln0_w=_f32(ln0_w), ln0_b=_f32(ln0_b), ln1_w=_f32(ln1_w), ln1_b=_f32(ln1_b))
+        rows = int(in_index.shape[0]) if in_index is not None else int(in_s.shape[0])
+        arena, offs = pack_weights(prog.gvps, weights, dev)
+        t["out_s"] = torch.empty(rows, prog.out_s, dtype=torch.float32, device=dev)
+        t["out_v"] = torch.empty(rows, prog.out_v, 3, dtype=torch.float32, device=dev)
+        a, blocks = _row_args(prog, rows, t, arena, offs)
+        check(lib().cgvp_rows_fwd(C.byref(prog.desc), C.byref(a), None, 0, _stream()), "cgvp_rows_fwd")
+        ctx.prog, ctx.t, ctx.arena, ctx.offs, ctx.rows = prog, t, arena, offs, rows
+        ctx.weights = weights
+        ctx.in_rows = int(in_s.shape[0])
+        ctx.mark_non_differentiable(*([] if prog.out_v else [t["out_v"]]))
+        return t["out_s"], t["out_v"]
+
+    @staticmethod
+    def backward(ctx, d_out_s, d_out_v):
+        prog, t, rows = ctx.prog, dict(ctx.t), ctx.rows
+        dev = t["in_s"].device
+        need = ctx.needs_input_grad
+        g = _lib.RowGradArgs()
+        d_out_s = _f32(d_out_s)
+        d_out_v = _f32(d_out_v) if prog.out_v else None
+        keep = [d_out_s, d_out_v]
+        g.d_out_s, g.d_out_v = d_out_s.data_ptr(), None if d_out_v is None else d_out_v.data_ptr()
+        d_in_s = d_in_v = d_h_s = d_h_v = None
+        gathered = t["in_index"] is not None
+        alloc = torch.zeros if gathered else torch.empty
+        if need[1]:
+            d_in_s = alloc(ctx.in_rows, prog.in_s, dtype=torch.float32, device=dev)
+            g.d_in_s = d_in_s.data_ptr()
+        if need[2] and prog.in_v:
+            d_in_v = alloc(ctx.in_rows, prog.in_v, 3, dtype=torch.float32, device=dev)
+            g.d_in_v = d_in_v.data_ptr()
+        if prog.residual_in and (need[5] or need[6]):
+            d_h_s = torch.empty(rows, prog.in_s, dtype=torch.float32, device=dev)
+            d_h_v = torch.empty(rows, prog.in_v, 3, dtype=torch.float32, device=dev)
+            g.d_h_s, g.d_h_v = d_h_s.data_ptr(), d_h_v.data_ptr()
+        lng = [None] * 4
+        if prog.pre_norm:
+            lng[0], lng[1] = torch.empty_like(t["ln0_w"]), torch.empty_like(t["ln0_b"])
+            g.d_ln0_w, g.d_ln0_b = lng[0].data_ptr(), lng[1].data_ptr()
+        if prog.post_norm:
+            lng[2], lng[3] = torch.empty_like(t["ln1_w"]), torch.empty_like(t["ln1_b"])
+            g.d_ln1_w, g.d_ln1_b = lng[2].data_ptr(), lng[3].data_ptr()
+        total = sum((sp.packed_floats() + 3) // 4 * 4 for sp in prog.gvps)
+        pg = torch.empty(max(total, 4), dtype=torch.float32, device=dev)
+        gblocks = (C.c_void_p * max(len(ctx.offs), 1))(*[pg.data_ptr() + 4 * o for o in ctx.offs])
+        g.h_packed_grads = C.addressof(gblocks)
+        t["out_s"] = t["out_v"] = None
+        a, blocks = _row_args(prog, rows, t, ctx.arena, ctx.offs)
+        nbytes = lib().cgvp_rows_workspace_bytes(C.byref(prog.desc), rows, 1)
+        ws = _workspace(nbytes, dev)
+        wp, wn = _aligned_ptr(ws)
+        check(lib().cgvp_rows_bwd(C.byref(prog.desc), C.byref(a), C.byref(g), wp, wn, _stream()), "cgvp_rows_bwd")
+        dw = unpack_grads(prog.gvps, pg, ctx.offs, ctx.weights)
+        del keep
+        return (None, d_in_s, d_in_v, None, None, d_h_s, d_h_v, None, None, None, None, *lng, *dw)
+
+
+def run_rows(prog, in_s, in_v=None, types=None, in_index=None, h=None, masks0=None, masks1=None, ln0=None, ln1=None,
+             weights=()):
+    h_s, h_v = (None, None) if h is None else h
+    m0s, m0v = (None, None) if masks0 is None else masks0
+    m1s, m1v = (None, None) if masks1 is None else masks1
+    l0w, l0b = (None, None) if ln0 is None else ln0
+    l1w, l1b = (None, None) if ln1 is None else ln1
+    return RowsFunction.apply(prog, in_s, in_v, types, in_index, h_s, h_v, m0s, m0v, m1s, m1v, l0w, l0b, l1w, l1b,
+                              *weights)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ConvProgram:
+    """Static description of a fused GVPConv (`CgvpConvDesc`)."""
+
+    def __init__(self, ns, nv, es, ev, gvps, aggr, edge_sorted=False):
+        assert 1 <= len(gvps) <= _lib.MAX_CHAIN
+        self.ns, self.nv, self.es, self.ev, self.gvps = int(ns), int(nv), int(es), int(ev), list(gvps)
+        self.out_s, self.out_v = gvps[-1].so, gvps[-1].vo
+        d = _lib.ConvDesc()
+        d.ns, d.nv, d.es, d.ev, d.n_gvp = self.ns, self.nv, self.es, self.ev, len(gvps)
+        for i, g in enumerate(gvps):
+            d.gvp[i] = g.desc()
+        d.aggr = _lib.AGGR_MEAN if aggr == "mean" else _lib.AGGR_SUM
+        d.edge_sorted = int(bool(edge_sorted))
+        self.desc = d
+
+
+class ConvFunction(torch.autograd.Function):
+    """autograd wrapper of cgvp_conv_fwd / cgvp_conv_bwd."""
+
+    @staticmethod
+    def forward(ctx, prog, plan, x_s, x_v, e_s, e_v, *weights):
+        dev = x_s.device
+        x_s, x_v, e_s, e_v = _f32(x_s), _f32(x_v), _f32(e_s), _f32(e_v)
+        arena, offs = pack_weights(prog.gvps, weights, dev)
+        out_s = torch.empty(plan.N, prog.out_s, dtype=torch.float32, device=dev)
+        out_v = torch.empty(plan.N, prog.out_v, 3, dtype=torch.float32, device=dev)
+        blocks = (C.c_void_p * len(offs))(*[arena.data_ptr() + 4 * o for o in offs])
+        nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 0)
+        ws = _workspace(nbytes, dev)
+        wp, wn = _aligned_ptr(ws)
+        check(lib().cgvp_conv_fwd(C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
+                                  _ptr(out_s), _ptr(out_v), wp, wn, _stream()), "cgvp_conv_fwd")
+        ctx.prog, ctx.plan, ctx.saved, ctx.arena, ctx.offs, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), arena, offs, weights
+        ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
+        return out_s, out_v
+
+    @staticmethod
+    def backward(ctx, d_out_s, d_out_v):
+        prog, plan = ctx.prog, ctx.plan
+        x_s, x_v, e_s, e_v = ctx.saved
+        dev = x_s.device
+        d_out_s, d_out_v = _f32(d_out_s), _f32(d_out_v)
+        d_x_s, d_x_v = torch.empty_like(x_s), torch.empty_like(x_v)
+        d_e_s, d_e_v = torch.empty_like(e_s), torch.empty_like(e_v)
+        total = sum((sp.packed_floats() + 3) // 4 * 4 for sp in prog.gvps)
+        pg = torch.empty(max(total, 4), dtype=torch.float32, device=dev)
+        blocks = (C.c_void_p * len(ctx.offs))(*[ctx.arena.data_ptr() + 4 * o for o in ctx.offs])
+        gblocks = (C.c_void_p * len(ctx.offs))(*[pg.data_ptr() + 4 * o for o in ctx.offs])
+        nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 1)
+        ws = _workspace(nbytes, dev)
+        wp, wn = _aligned_ptr(ws)
+        check(lib().cgvp_conv_bwd(C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
+                                  _ptr(d_out_s), _ptr(d_out_v), _ptr(d_x_s), _ptr(d_x_v), _ptr(d_e_s), _ptr(d_e_v), 0,
+                                  gblocks, wp, wn, _stream()), "cgvp_conv_bwd")
+        dw = unpack_grads(prog.gvps, pg, ctx.offs, ctx.weights)
+        return (None, None, d_x_s, d_x_v, d_e_s, d_e_v, *dw)
+
+
+def run_conv(prog, plan, x, edge_attr, weights):
+    return ConvFunction.apply(prog, plan, x[0], x[1], edge_attr[0], edge_attr[1], *weights)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def gather_message_input(edge_index, x, edge_attr):
+    """Stand-alone gather: (ms [E, 2ns+es], mv [E, 2nv+ev, 3]) as GVPConv.message builds them (gvp_layers.py:306)."""
+    s, v = _f32(x[0]), _f32(x[1])
+    es, ev = _f32(edge_attr[0]), _f32(edge_attr[1])
+    ei = edge_index.contiguous().long()
+    e = int(ei.shape[1])
+    ns, nv, nes, nev = s.shape[1], v.shape[1], es.shape[1], ev.shape[1]
+    ms = torch.empty(e, 2 * ns + nes, dtype=torch.float32, device=s.device)
+    mv = torch.empty(e, 2 * nv + nev, 3, dtype=torch.float32, device=s.device)
+    check(lib().cgvp_gather_message_input(_ptr(ei), e, ns, nv, nes, nev, _ptr(s), _ptr(v), _ptr(es), _ptr(ev), _ptr(ms),
+                                          _ptr(mv), _stream()), "cgvp_gather_message_input")
+    return ms, mv
+
+
+def segment_reduce(rows, plan, aggr="sum", use_perm=True, out=None, beta=0):
+    """Deterministic aggregation of per-edge rows at their target node (rows in ORIGINAL edge order if use_perm)."""
+    rows = _f32(rows)
+    width = rows.shape[1]
+    if out is None:
+        out = torch.empty(plan.N, width, dtype=torch.float32, device=rows.device)
+    code = _lib.AGGR_MEAN if aggr == "mean" else _lib.AGGR_SUM
+    check(lib().cgvp_segment_reduce(_ptr(rows), width, _ptr(plan.rowptr), _ptr(plan.perm) if use_perm else None, plan.N,
+                                    code, int(beta), _ptr(out), _stream()), "cgvp_segment_reduce")
+    return out
