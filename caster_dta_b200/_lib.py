@@ -64,6 +64,8 @@ SIGNATURES = {
     "cgvp_last_error": (C.c_char_p, []),
     "cgvp_version": (C.c_int32, []),
     "cgvp_sm_count": (C.c_int32, []),
+    "cgvp_profile_enable": (C.c_int32, [C.c_int32]),
+    "cgvp_profile_collect": (C.c_int32, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cgvp_gvp_packed_floats": (C.c_int64, [C.POINTER(GvpDesc)]),
     "cgvp_pack_weights": (C.c_int32, [C.c_int32, C.POINTER(GvpDesc), C.POINTER(GvpWeights), C.POINTER(C.c_void_p),
                                       C.c_void_p]),
@@ -94,6 +96,24 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
+KERNEL_IDS = {"conv_fwd": 0, "conv_bwd": 1, "rows_fwd": 2, "rows_bwd": 3, "segment_reduce": 4, "gather": 5,
+              "featurize": 6}
+
+
+def profile_enable(on):
+    lib().cgvp_profile_enable(int(on))
+
+
+def profile_collect():
+    """{kernel name: (total ms, launches)} for everything recorded since profile_enable(True)."""
+    out = {}
+    for name, kid in KERNEL_IDS.items():
+        ms, n = C.c_double(0), C.c_int64(0)
+        lib().cgvp_profile_collect(kid, C.byref(ms), C.byref(n))
+        out[name] = (ms.value, n.value)
+    return out
+
+
 _lib = None
 LAUNCHES = 0   # number of library calls that enqueue kernels (bench.py reports it)
 
@@ -112,6 +132,25 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+# optional per-entry-point device timing (bench.py): name -> list of (start_event, end_event)
+TIMED = None          # set to a set of entry-point names to time, e.g. {"cgvp_conv_bwd"}
+EVENTS = {}
+
+
+def timed_call(what, fn, *args):
+    """Call a C-ABI entry point, optionally bracketed by CUDA events on the current stream."""
+    if TIMED is not None and what in TIMED:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        EVENTS.setdefault(what, []).append((a, b))
+    else:
+        rc = fn(*args)
+    check(rc, what)
 
 
 def check(rc, what):

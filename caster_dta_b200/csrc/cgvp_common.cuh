@@ -177,6 +177,10 @@ static inline GradCols plan_grad_cols(const GvpP* g, int n, int start_col) {
     return c;
 }
 
+// optional event bracketing of the main kernels (see cgvp_profile_enable)
+void cgvp_prof_begin(int kernel_id, cudaStream_t st);
+void cgvp_prof_end(int kernel_id, cudaStream_t st);
+
 int cgvp_max_smem_optin();
 int cgvp_num_sms();
 

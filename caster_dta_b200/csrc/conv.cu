@@ -368,7 +368,7 @@ static int conv_geometry(ConvK& K, int smem_max, bool backward, size_t* smem_byt
         const int wbytes = pass == 0 ? wt_full * 4 : 0;
         const auto need = [&](int R) { return (size_t)wbytes + (size_t)(4 * R + 4) * 4 + (size_t)K.ncols * (R + 1) * 16 + 16; };
         int best_r = 0, best_c = 0;
-        for (int R = CGVP_THREADS; R >= 32; R -= 32) {
+        for (int R = CGVP_THREADS; R >= 8; R = R > 32 ? R - 32 : R / 2) {   // 128, 96, 64, 32, 16, 8
             const size_t n = need(R);
             if (n > (size_t)smem_max) continue;
             int c = (int)((size_t)(228 * 1024) / (n + 1024));
@@ -391,7 +391,7 @@ static int conv_geometry(ConvK& K, int smem_max, bool backward, size_t* smem_byt
 
 static int64_t conv_ws_layout(const ConvK& K, int64_t E, int64_t N, bool backward, int grid, int64_t* o_head,
                               int64_t* o_tail, int64_t* o_cnt, int64_t* o_dj, int64_t* o_partial, int64_t* o_reduced) {
-    const int64_t ntiles_max = cdiv64(E > 0 ? E : 1, 32);
+    const int64_t ntiles_max = cdiv64(E > 0 ? E : 1, 8);
     const int CH = (K.so + 3 * K.vo) > (K.ns + 3 * K.nv) ? (K.so + 3 * K.vo) : (K.ns + 3 * K.nv);
     int64_t off = 0;
     *o_head = off; off += align_up(ntiles_max * CH * 4, 256);
@@ -418,7 +418,8 @@ extern "C" int64_t cgvp_conv_workspace_bytes(const CgvpConvDesc* desc, int64_t n
 static int conv_common_checks(const ConvK& K, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                               const float* e_v, const float* const* h_packed) {
     CGVP_REQUIRE(plan && plan->num_edges >= 0 && plan->num_nodes >= 0, "conv: null plan");
-    CGVP_REQUIRE(x_s && (K.nv == 0 || x_v) && (K.es == 0 || e_s) && (K.ev == 0 || e_v), "conv: null input tensor");
+    if (plan->num_edges > 0 && plan->num_nodes > 0)
+        CGVP_REQUIRE(x_s && (K.nv == 0 || x_v) && (K.es == 0 || e_s) && (K.ev == 0 || e_v), "conv: null input tensor");
     CGVP_REQUIRE(h_packed, "conv: packed weights missing");
     for (int k = 0; k < K.n_gvp; ++k)
         CGVP_REQUIRE(h_packed[k] && ((uintptr_t)h_packed[k] & 15) == 0, "conv: packed block %d null/unaligned", k);
@@ -462,6 +463,7 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
     K.x_s = x_s; K.x_v = x_v; K.e_s = e_s; K.e_v = e_v; K.out_s = out_s; K.out_v = out_v;
     K.vec_x = ((uintptr_t)x_s & 15) == 0; K.vec_e = ((uintptr_t)e_s & 15) == 0;
     for (int k = 0; k < K.n_gvp; ++k) K.wp[k] = h_packed[k];
+    cgvp_prof_begin(CGVP_K_CONV_FWD, st);
     if (K.w_smem) {
         CGVP_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_fwd_kernel<true><<<grid, CGVP_THREADS, smem, st>>>(K);
@@ -469,6 +471,7 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
         CGVP_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_fwd_kernel<false><<<grid, CGVP_THREADS, smem, st>>>(K);
     }
+    cgvp_prof_end(CGVP_K_CONV_FWD, st);
     CGVP_LAUNCH_CHECK("conv_fwd_kernel");
     return 0;
 }
@@ -519,6 +522,7 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
         K.out_s = d_x_s; K.out_v = d_x_v;
         K.d_out_s = d_out_s; K.d_out_v = d_out_v; K.d_e_s = d_e_s; K.d_e_v = d_e_v; K.acc_edge = accumulate_edge;
         for (int k = 0; k < K.n_gvp; ++k) K.wp[k] = h_packed[k];
+        cgvp_prof_begin(CGVP_K_CONV_BWD, st);
         if (K.w_smem) {
             CGVP_CUDA(cudaFuncSetAttribute(conv_bwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             conv_bwd_kernel<2, true><<<grid, CGVP_THREADS, smem, st>>>(K);
@@ -526,6 +530,7 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
             CGVP_CUDA(cudaFuncSetAttribute(conv_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             conv_bwd_kernel<2, false><<<grid, CGVP_THREADS, smem, st>>>(K);
         }
+        cgvp_prof_end(CGVP_K_CONV_BWD, st);
         CGVP_LAUNCH_CHECK("conv_bwd_kernel");
         // d_x += sum over outgoing edges of the source-side slice (deterministic, source CSR view)
         const int rc = cgvp_segment_reduce_split(K.dj, K.ns + 3 * K.nv, plan->srowptr, plan->sperm, N, CGVP_AGGR_SUM, 1,

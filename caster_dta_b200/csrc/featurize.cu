@@ -252,7 +252,9 @@ extern "C" int32_t cgvp_featurize_fill(const float* ca, const int64_t* ptr, int6
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
     int64_t blocks = cdiv64(num_nodes, FEAT_WARPS);
     if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    cgvp_prof_begin(CGVP_K_FEATURIZE, (cudaStream_t)stream);
     feat_fill_kernel<<<(int)blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(K);
+    cgvp_prof_end(CGVP_K_FEATURIZE, (cudaStream_t)stream);
     CGVP_LAUNCH_CHECK("feat_fill_kernel");
     return 0;
 }

@@ -36,6 +36,56 @@ int cgvp_validate_gvp(const CgvpGvpDesc& d, const char* what) {
     return 0;
 }
 
+// ---- kernel timing -------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+struct ProfRec { int id; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_open[CGVP_K_COUNT];
+
+void cgvp_prof_begin(int id, cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    cudaEventRecord(a, st);
+    g_prof_open[id] = a;
+}
+void cgvp_prof_end(int id, cudaStream_t st) {
+    if (!g_prof_on || !g_prof_open[id]) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof.size() < 65536) g_prof.push_back({id, g_prof_open[id], b});
+    g_prof_open[id] = nullptr;
+}
+extern "C" int32_t cgvp_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int32_t cgvp_profile_collect(int32_t kernel_id, double* total_ms, int64_t* launches) {
+    CGVP_REQUIRE(kernel_id >= 0 && kernel_id < CGVP_K_COUNT && total_ms && launches, "profile_collect: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    int64_t n = 0;
+    std::vector<ProfRec> keep;
+    for (auto& r : g_prof) {
+        if (r.id != kernel_id) { keep.push_back(r); continue; }
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; ++n; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.swap(keep);
+    *total_ms = tot; *launches = n;
+    return 0;
+}
+
 extern "C" const char* cgvp_last_error(void) { return g_err; }
 extern "C" int32_t cgvp_version(void) { return 100; }
 extern "C" int32_t cgvp_sm_count(void) { return cgvp_num_sms(); }

@@ -139,6 +139,7 @@ extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t 
     CGVP_REQUIRE(edge_index, "gather: null edge_index");
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
+    cgvp_prof_begin(CGVP_K_GATHER, st);
     if (2 * ns + es > 0) {
         CGVP_REQUIRE(ms && (ns == 0 || s) && (es == 0 || e_s), "gather: null scalar buffer");
         const bool vec = ns % 4 == 0 && es % 4 == 0 && (((uintptr_t)s | (uintptr_t)e_s | (uintptr_t)ms) & 15) == 0;
@@ -155,6 +156,7 @@ extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t 
         gather_vector_kernel<<<grid, 256, 0, st>>>(edge_index, num_edges, nv, ev, v, e_v, mv);
         CGVP_LAUNCH_CHECK("gather_vector_kernel");
     }
+    cgvp_prof_end(CGVP_K_GATHER, st);
     return 0;
 }
 
@@ -202,8 +204,10 @@ int cgvp_segment_reduce_split(const float* rows, int width, const int* rowptr, c
     const bool vec = width % 4 == 0 && ((uintptr_t)rows & 15) == 0;
     const int64_t total = N * (width / (vec ? 4 : 1));
     const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
+    cgvp_prof_begin(CGVP_K_SEGMENT_REDUCE, st);
     if (vec) segment_reduce_kernel<4><<<grid, 256, 0, st>>>(rows, width, rowptr, index, N, aggr, beta, out_a, wa, out_b, wb);
     else segment_reduce_kernel<1><<<grid, 256, 0, st>>>(rows, width, rowptr, index, N, aggr, beta, out_a, wa, out_b, wb);
+    cgvp_prof_end(CGVP_K_SEGMENT_REDUCE, st);
     CGVP_LAUNCH_CHECK("segment_reduce_kernel");
     return 0;
 }

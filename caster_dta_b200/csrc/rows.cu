@@ -391,7 +391,7 @@ static int build_rows_k(const CgvpRowDesc* desc, bool backward, RowsK& K) {
 static int choose_geometry(RowsK& K, int smem_max, size_t* smem_bytes) {
     for (int pass = 0; pass < 2; ++pass) {
         const int wbytes = pass == 0 ? K.wtotal * 4 : 0;
-        for (int R = CGVP_THREADS; R >= 32; R -= 32) {
+        for (int R = CGVP_THREADS; R >= 8; R = R > 32 ? R - 32 : R / 2) {   // 128, 96, 64, 32, 16, 8
             const size_t need = (size_t)wbytes + (size_t)R * 4 + (size_t)K.ncols * (R + 1) * 16 + 16;
             if (need <= (size_t)smem_max) {
                 K.R = R; K.rp = R + 1; K.w_smem = pass == 0;
@@ -444,6 +444,7 @@ extern "C" int32_t cgvp_rows_fwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     const int grid = K.ntiles < sms * per_sm ? K.ntiles : sms * per_sm;
+    cgvp_prof_begin(CGVP_K_ROWS_FWD, (cudaStream_t)stream);
     if (K.w_smem) {
         CGVP_CUDA(cudaFuncSetAttribute(rows_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rows_fwd_kernel<true><<<grid, CGVP_THREADS, smem, (cudaStream_t)stream>>>(K);
@@ -451,6 +452,7 @@ extern "C" int32_t cgvp_rows_fwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
         CGVP_CUDA(cudaFuncSetAttribute(rows_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rows_fwd_kernel<false><<<grid, CGVP_THREADS, smem, (cudaStream_t)stream>>>(K);
     }
+    cgvp_prof_end(CGVP_K_ROWS_FWD, (cudaStream_t)stream);
     CGVP_LAUNCH_CHECK("rows_fwd_kernel");
     return 0;
 }
@@ -485,6 +487,7 @@ extern "C" int32_t cgvp_rows_bwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
     if (K.partial_floats > 0) CGVP_CUDA(cudaMemsetAsync(ws, 0, (size_t)need, st));
     if (args->rows > 0) {
         // two register-resident 4x4 weight-gradient blocks per thread; larger chains spill to the global partial
+        cgvp_prof_begin(CGVP_K_ROWS_BWD, st);
         if (K.w_smem) {
             CGVP_CUDA(cudaFuncSetAttribute(rows_bwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             rows_bwd_kernel<2, true><<<grid, CGVP_THREADS, smem, st>>>(K);
@@ -492,6 +495,7 @@ extern "C" int32_t cgvp_rows_bwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
             CGVP_CUDA(cudaFuncSetAttribute(rows_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             rows_bwd_kernel<2, false><<<grid, CGVP_THREADS, smem, st>>>(K);
         }
+        cgvp_prof_end(CGVP_K_ROWS_BWD, st);
         CGVP_LAUNCH_CHECK("rows_bwd_kernel");
     }
     if (K.partial_floats > 0) {

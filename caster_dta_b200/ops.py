@@ -92,7 +92,7 @@ def pack_weights(specs, weights, device):
         for name, t in zip(("wh", "ws", "bs", "wv", "wsv", "bg"), w):
             setattr(wts[i], name, None if t is None else t.data_ptr())
     blocks = (C.c_void_p * n)(*[arena.data_ptr() + 4 * o for o in offs])
-    check(lib().cgvp_pack_weights(n, descs, wts, blocks, _stream()), "cgvp_pack_weights")
+    _lib.timed_call("cgvp_pack_weights", lib().cgvp_pack_weights, n, descs, wts, blocks, _stream())
     return arena, offs
 
 
@@ -111,7 +111,7 @@ def unpack_grads(specs, packed_grads, offs, weights):
             out.append(g)
             setattr(gr[i], name, None if g is None else g.data_ptr())
     blocks = (C.c_void_p * n)(*[packed_grads.data_ptr() + 4 * o for o in offs])
-    check(lib().cgvp_unpack_grads(n, descs, blocks, gr, _stream()), "cgvp_unpack_grads")
+    _lib.timed_call("cgvp_unpack_grads", lib().cgvp_unpack_grads, n, descs, blocks, gr, _stream())
     return out
 
 
@@ -212,7 +212,7 @@ class RowsFunction(torch.autograd.Function):
         t["out_s"] = torch.empty(rows, prog.out_s, dtype=torch.float32, device=dev)
         t["out_v"] = torch.empty(rows, prog.out_v, 3, dtype=torch.float32, device=dev)
         a, blocks = _row_args(prog, rows, t, arena, offs)
-        check(lib().cgvp_rows_fwd(C.byref(prog.desc), C.byref(a), None, 0, _stream()), "cgvp_rows_fwd")
+        _lib.timed_call("cgvp_rows_fwd", lib().cgvp_rows_fwd, C.byref(prog.desc), C.byref(a), None, 0, _stream())
         ctx.prog, ctx.t, ctx.arena, ctx.offs, ctx.rows = prog, t, arena, offs, rows
         ctx.weights = weights
         ctx.in_rows = int(in_s.shape[0])
@@ -258,7 +258,7 @@ class RowsFunction(torch.autograd.Function):
         nbytes = lib().cgvp_rows_workspace_bytes(C.byref(prog.desc), rows, 1)
         ws = _workspace(nbytes, dev)
         wp, wn = _aligned_ptr(ws)
-        check(lib().cgvp_rows_bwd(C.byref(prog.desc), C.byref(a), C.byref(g), wp, wn, _stream()), "cgvp_rows_bwd")
+        _lib.timed_call("cgvp_rows_bwd", lib().cgvp_rows_bwd, C.byref(prog.desc), C.byref(a), C.byref(g), wp, wn, _stream())
         dw = unpack_grads(prog.gvps, pg, ctx.offs, ctx.weights)
         del keep
         return (None, d_in_s, d_in_v, None, None, d_h_s, d_h_v, None, None, None, None, *lng, *dw)
@@ -306,8 +306,8 @@ class ConvFunction(torch.autograd.Function):
         nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 0)
         ws = _workspace(nbytes, dev)
         wp, wn = _aligned_ptr(ws)
-        check(lib().cgvp_conv_fwd(C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
-                                  _ptr(out_s), _ptr(out_v), wp, wn, _stream()), "cgvp_conv_fwd")
+        _lib.timed_call("cgvp_conv_fwd", lib().cgvp_conv_fwd, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
+                                  _ptr(out_s), _ptr(out_v), wp, wn, _stream())
         ctx.prog, ctx.plan, ctx.saved, ctx.arena, ctx.offs, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), arena, offs, weights
         ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
         return out_s, out_v
@@ -327,9 +327,9 @@ class ConvFunction(torch.autograd.Function):
         nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 1)
         ws = _workspace(nbytes, dev)
         wp, wn = _aligned_ptr(ws)
-        check(lib().cgvp_conv_bwd(C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
+        _lib.timed_call("cgvp_conv_bwd", lib().cgvp_conv_bwd, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
                                   _ptr(d_out_s), _ptr(d_out_v), _ptr(d_x_s), _ptr(d_x_v), _ptr(d_e_s), _ptr(d_e_v), 0,
-                                  gblocks, wp, wn, _stream()), "cgvp_conv_bwd")
+                                  gblocks, wp, wn, _stream())
         dw = unpack_grads(prog.gvps, pg, ctx.offs, ctx.weights)
         return (None, None, d_x_s, d_x_v, d_e_s, d_e_v, *dw)
 

@@ -57,6 +57,15 @@ const char* cgvp_last_error(void);
 int32_t cgvp_version(void);
 int32_t cgvp_sm_count(void); /* SMs of the current device (grid sizing), 0 if no device */
 
+/* ---- kernel timing (measurement aid; no reference counterpart) ------------------------------------------------
+ * When enabled, the library brackets the MAIN kernel of each operator with cudaEvents on the caller's stream.
+ * cgvp_profile_collect synchronises on the recorded events and returns the summed device time and the launch
+ * count of one kernel id, then forgets those records. */
+enum { CGVP_K_CONV_FWD = 0, CGVP_K_CONV_BWD = 1, CGVP_K_ROWS_FWD = 2, CGVP_K_ROWS_BWD = 3, CGVP_K_SEGMENT_REDUCE = 4,
+       CGVP_K_GATHER = 5, CGVP_K_FEATURIZE = 6, CGVP_K_COUNT = 7 };
+int32_t cgvp_profile_enable(int32_t on);
+int32_t cgvp_profile_collect(int32_t kernel_id, double* total_ms, int64_t* launches);
+
 /* ---- weight packing ----------------------------------------------------------------------------------------
  * Kernels consume weights in a packed, zero-padded, K-major layout (and its transpose for the backward data path).
  * cgvp_gvp_packed_floats: floats of one packed GVP block.  cgvp_pack_weights: PyTorch layout -> packed blocks
