@@ -45,9 +45,13 @@ void cgvp_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
-static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+#define CGVP_HD __host__ __device__
+constexpr CGVP_HD inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+constexpr CGVP_HD inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+constexpr CGVP_HD inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+constexpr CGVP_HD inline int imax(int a, int b) { return a > b ? a : b; }
+// opt-in dynamic shared memory per block on sm_100 (227 KB); the specialised kernels size their tiles against it
+#define CGVP_SMEM_OPTIN 232448
 
 // ---- packed GVP parameters --------------------------------------------------------------------------------------
 // Forward half (also the layout of the weight-gradient block), all K-major with the output index contiguous:
@@ -69,9 +73,8 @@ struct GvpP {
     int o_wh_b, o_ws_b, o_wv_b, o_wsv_b, total_floats;
 };
 
-static inline GvpP make_gvp_p(const CgvpGvpDesc& d) {
-    GvpP g;
-    memset(&g, 0, sizeof(g));
+constexpr CGVP_HD inline GvpP make_gvp_p(const CgvpGvpDesc& d) {
+    GvpP g{};
     g.si = d.si; g.vi = d.vi; g.so = d.so; g.vo = d.vo;
     g.h = d.vi > 0 ? d.h : 0;
     g.sact = d.scalar_act; g.vact = d.vector_act; g.gate = (d.vector_gate && d.vi > 0 && d.vo > 0) ? 1 : 0;
@@ -108,16 +111,13 @@ struct ChainCols {
 };
 
 // distinct = every stage keeps its own buffers (needed by backward); otherwise stages ping-pong.
-static inline ChainCols plan_chain_cols(const GvpP* g, int n, bool distinct, bool saves, int start_col) {
-    ChainCols c;
-    memset(&c, 0, sizeof(c));
+constexpr CGVP_HD inline ChainCols plan_chain_cols(const GvpP* g, int n, bool distinct, bool saves, int start_col) {
+    ChainCols c{};
     int col = start_col;
-    auto scols = [&](int k) { return k < n ? g[k].ks4 : g[n - 1].so4; };
-    auto vpcs = [&](int k) { return k < n ? g[k].vi4 : g[n - 1].vo4; };
     if (distinct) {
         for (int k = 0; k <= n; ++k) {
-            c.s[k] = col; col += scols(k);
-            c.vpc[k] = vpcs(k); c.v[k] = col; col += 3 * c.vpc[k];
+            c.s[k] = col; col += k < n ? g[k].ks4 : g[n - 1].so4;
+            c.vpc[k] = k < n ? g[k].vi4 : g[n - 1].vo4; c.v[k] = col; col += 3 * c.vpc[k];
         }
         for (int k = 0; k < n; ++k) {
             c.vhpc[k] = g[k].h4; c.vh[k] = col; col += 3 * g[k].h4;
@@ -130,49 +130,22 @@ static inline ChainCols plan_chain_cols(const GvpP* g, int n, bool distinct, boo
     } else {
         int smax[2] = {0, 0}, vmax[2] = {0, 0}, vhmax = 0, spmax = 0;
         for (int k = 0; k <= n; ++k) {
-            if (scols(k) > smax[k & 1]) smax[k & 1] = scols(k);
-            if (3 * vpcs(k) > vmax[k & 1]) vmax[k & 1] = 3 * vpcs(k);
+            const int sc = k < n ? g[k].ks4 : g[n - 1].so4, vc = 3 * (k < n ? g[k].vi4 : g[n - 1].vo4);
+            smax[k & 1] = imax(smax[k & 1], sc);
+            vmax[k & 1] = imax(vmax[k & 1], vc);
         }
         for (int k = 0; k < n; ++k) {
-            if (3 * g[k].h4 > vhmax) vhmax = 3 * g[k].h4;
-            if (g[k].ksv4 > spmax) spmax = g[k].ksv4;
+            vhmax = imax(vhmax, 3 * g[k].h4);
+            spmax = imax(spmax, g[k].ksv4);
         }
-        int sreg[2], vreg[2];
+        int sreg[2] = {0, 0}, vreg[2] = {0, 0};
         sreg[0] = col; col += smax[0]; vreg[0] = col; col += vmax[0];
         sreg[1] = col; col += smax[1]; vreg[1] = col; col += vmax[1];
-        int vhreg = col; col += vhmax;
-        int spreg = col; col += spmax;
-        for (int k = 0; k <= n; ++k) { c.s[k] = sreg[k & 1]; c.v[k] = vreg[k & 1]; c.vpc[k] = vpcs(k); }
+        const int vhreg = col; col += vhmax;
+        const int spreg = col; col += spmax;
+        for (int k = 0; k <= n; ++k) { c.s[k] = sreg[k & 1]; c.v[k] = vreg[k & 1]; c.vpc[k] = k < n ? g[k].vi4 : g[n - 1].vo4; }
         for (int k = 0; k < n; ++k) { c.vh[k] = vhreg; c.vhpc[k] = g[k].h4; c.sp[k] = spreg; }
     }
-    c.ncols = col - start_col;
-    return c;
-}
-
-// gradient scratch columns shared by all GVPs of a chain (backward)
-struct GradCols {
-    int gs[2], gv[2], gvpc;   // two (scalar, vector) gradient sets; GVP k reads set (k&1)^par and writes the other
-    int dg;                   // gate pre-activation gradient
-    int dvh, dvhpc;           // hidden vector gradient
-    int ncols;
-};
-
-static inline GradCols plan_grad_cols(const GvpP* g, int n, int start_col) {
-    GradCols c;
-    int smax = 0, vmax = 0, hmax = 0, vomax = 0;
-    for (int k = 0; k < n; ++k) {
-        if (g[k].ks4 > smax) smax = g[k].ks4;
-        if (g[k].so4 > smax) smax = g[k].so4;
-        if (g[k].vi4 > vmax) vmax = g[k].vi4;
-        if (g[k].vo4 > vmax) vmax = g[k].vo4;
-        if (g[k].h4 > hmax) hmax = g[k].h4;
-        if (g[k].vo4 > vomax) vomax = g[k].vo4;
-    }
-    int col = start_col;
-    c.gvpc = vmax;
-    for (int i = 0; i < 2; ++i) { c.gs[i] = col; col += smax; c.gv[i] = col; col += 3 * vmax; }
-    c.dg = col; col += vomax;
-    c.dvhpc = hmax; c.dvh = col; col += 3 * hmax;
     c.ncols = col - start_col;
     return c;
 }

@@ -42,6 +42,7 @@ template <int OB, int NP>
 __device__ __forceinline__ void rl_block(const float4* __restrict__ in, int pp, int rp, int k4n,
                                          const float* __restrict__ W, int ldw, int o0, float2 (&acc)[NP][OB / 2]) {
     const float* __restrict__ w = W + o0;
+#pragma unroll
     for (int k4 = 0; k4 < k4n; ++k4) {
         float4 x[NP];
 #pragma unroll
@@ -69,6 +70,7 @@ struct IC { static constexpr int value = N; };
 template <class F>
 __device__ __forceinline__ void for_blocks(int n4, F&& f) {
     int o4 = 0;
+#pragma unroll
     for (; n4 - o4 >= 4; o4 += 4) f(IC<16>{}, o4 * 4);
     if (n4 - o4 >= 2) { f(IC<8>{}, o4 * 4); o4 += 2; }
     if (n4 - o4 >= 1) f(IC<4>{}, o4 * 4);
@@ -91,8 +93,8 @@ struct StageIO {
     int vo, sg;                  // saves for backward: pre-gate V', gate value
 };
 
-static inline __host__ __device__ StageIO stage_io(const ChainCols& c, int k) {
-    StageIO s;
+constexpr CGVP_HD inline StageIO stage_io(const ChainCols& c, int k) {
+    StageIO s{};
     s.s_in = c.s[k]; s.v_in = c.v[k]; s.v_in_pc = c.vpc[k];
     s.vh = c.vh[k]; s.vh_pc = c.vhpc[k]; s.sp = c.sp[k];
     s.s_out = c.s[k + 1]; s.v_out = c.v[k + 1]; s.v_out_pc = c.vpc[k + 1];
@@ -423,7 +425,7 @@ struct DwPlan {
     DwMat m[CGVP_MAX_DWMAT];
 };
 
-static inline void dw_add(DwPlan& p, int col_a, int pitch_a, int na4, int col_b, int pitch_b, int nb4, int np, int goff) {
+constexpr CGVP_HD inline void dw_add(DwPlan& p, int col_a, int pitch_a, int na4, int col_b, int pitch_b, int nb4, int np, int goff) {
     if (na4 <= 0 || nb4 <= 0) return;
     DwMat& m = p.m[p.nmat++];
     m.col_a = col_a; m.pitch_a = pitch_a; m.na4 = na4; m.col_b = col_b; m.pitch_b = pitch_b; m.nb4 = nb4;
@@ -432,7 +434,7 @@ static inline void dw_add(DwPlan& p, int col_a, int pitch_a, int na4, int col_b,
 }
 
 // forward operands (A) and gradient operands (B) of GVP `g` with stage columns c / gradient columns d
-static inline void dw_add_gvp(DwPlan& p, const GvpP& g, const StageIO& c, const GradIO& d, int goff) {
+constexpr CGVP_HD inline void dw_add_gvp(DwPlan& p, const GvpP& g, const StageIO& c, const GradIO& d, int goff) {
     if (g.vi > 0) dw_add(p, c.v_in, c.v_in_pc, g.vi4, d.dvh, d.dvh_pc, g.h4, 3, goff + g.o_wh_t);
     dw_add(p, c.s_in, 0, g.ks4, d.gs_in, 0, g.so4, 1, goff + g.o_ws_t);
     if (g.vi > 0 && g.vo > 0) dw_add(p, c.vh, c.vh_pc, g.h4, d.gv_in, d.gv_in_pc, g.vo4, 3, goff + g.o_wv_t);
