@@ -64,6 +64,7 @@ SIGNATURES = {
     "cgvp_last_error": (C.c_char_p, []),
     "cgvp_version": (C.c_int32, []),
     "cgvp_sm_count": (C.c_int32, []),
+    "cgvp_set_fast_paths": (C.c_int32, [C.c_int32]),
     "cgvp_profile_enable": (C.c_int32, [C.c_int32]),
     "cgvp_profile_collect": (C.c_int32, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cgvp_gvp_packed_floats": (C.c_int64, [C.POINTER(GvpDesc)]),
@@ -98,6 +99,11 @@ SIGNATURES = {
 
 KERNEL_IDS = {"conv_fwd": 0, "conv_bwd": 1, "rows_fwd": 2, "rows_bwd": 3, "segment_reduce": 4, "gather": 5,
               "featurize": 6}
+
+
+def set_fast_paths(on):
+    """1 (default): specialised register-resident kernels where compiled in; 0: generic tile kernels only."""
+    lib().cgvp_set_fast_paths(int(bool(on)))
 
 
 def profile_enable(on):

@@ -5,6 +5,14 @@
 
 using namespace cgvp;
 
+int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
+                     const float* e_v, const float* const* h_packed, float* out_s, float* out_v, float* part_head,
+                     float* part_tail, cudaStream_t st, int* rc_out);
+int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
+                     const float* e_v, const float* const* h_packed, const float* d_out_s, const float* d_out_v,
+                     float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
+                     float* part_tail, float* dj, float* partial, int max_grid, cudaStream_t st, int* grid_out, int* rc_out);
+
 int cgvp_segment_reduce_split(const float* rows, int width, const int* rowptr, const int* index, int64_t N, int aggr,
                               int beta, float* out_a, int wa, float* out_b, int wb, cudaStream_t st);
 
@@ -437,6 +445,17 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
     CGVP_REQUIRE(out_s && (K.vo == 0 || out_v), "conv_fwd: null output");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = plan->num_edges, N = plan->num_nodes;
+    if (E > 0 && N > 0) {   // register-resident specialised kernel for the dims it was compiled for (conv_reg.cu)
+        int64_t oh, ot, oc, od, op, orr;
+        const int64_t need = conv_ws_layout(K, E, N, false, 1, &oh, &ot, &oc, &od, &op, &orr);
+        if (ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0) {
+            char* base = reinterpret_cast<char*>(ws);
+            int rc = 0;
+            if (conv_fwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, reinterpret_cast<float*>(base + oh),
+                                 reinterpret_cast<float*>(base + ot), st, &rc))
+                return rc;
+        }
+    }
     // nodes without incoming edges receive 0 (PyG scatter with dim_size = N)
     if (N > 0) {
         CGVP_CUDA(cudaMemsetAsync(out_s, 0, (size_t)N * K.so * 4, st));
@@ -489,6 +508,29 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
     CGVP_REQUIRE(h_packed_grads, "conv_bwd: packed gradient blocks missing");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = plan->num_edges, N = plan->num_nodes;
+    if (E > 0 && N > 0 && plan->sperm && plan->srowptr) {   // specialised register-resident kernel (conv_reg.cu)
+        const int sms_ = cgvp_num_sms();
+        int64_t oh, ot, oc, od, op, orr;
+        const int64_t need = conv_ws_layout(K, E, N, true, sms_, &oh, &ot, &oc, &od, &op, &orr);
+        if (ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0) {
+            char* base = reinterpret_cast<char*>(ws);
+            float* dj = reinterpret_cast<float*>(base + od);
+            float* partial = reinterpret_cast<float*>(base + op);
+            int rc = 0, grid = 0;
+            if (conv_bwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, d_out_s, d_out_v, d_x_s, d_x_v, d_e_s, d_e_v,
+                                 accumulate_edge, reinterpret_cast<float*>(base + oh), reinterpret_cast<float*>(base + ot), dj,
+                                 partial, sms_, st, &grid, &rc)) {
+                if (rc) return rc;
+                rc = cgvp_segment_reduce_split(dj, K.ns + 3 * K.nv, plan->srowptr, plan->sperm, N, CGVP_AGGR_SUM, 1, d_x_s,
+                                               K.ns, d_x_v, 3 * K.nv, st);
+                if (rc) return rc;
+                CgvpSeg seg[CGVP_MAX_SEGS];
+                memset(seg, 0, sizeof(seg));
+                for (int k = 0; k < K.n_gvp; ++k) { seg[k].dst = h_packed_grads[k]; seg[k].off = K.goff[k]; seg[k].n = K.g[k].fwd_floats; }
+                return cgvp_reduce_partials(partial, grid, K.partial_floats, reinterpret_cast<float*>(base + orr), seg, K.n_gvp, st);
+            }
+        }
+    }
     if (N > 0) {
         CGVP_CUDA(cudaMemsetAsync(d_x_s, 0, (size_t)N * K.ns * 4, st));
         if (K.nv > 0) CGVP_CUDA(cudaMemsetAsync(d_x_v, 0, (size_t)N * K.nv * 12, st));

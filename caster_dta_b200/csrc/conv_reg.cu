@@ -1,0 +1,345 @@
+// Register-resident fused GVPConv for compile-time known dims (the CASTER-DTA checkpoint dims (16,4)/(32,1)).
+// Replaces GVPConv.forward/message + PyG propagate (models/gvp_layers.py:291-308) like conv.cu, but:
+//   * one thread = one dst-sorted edge, the whole message chain lives in registers (cgvp_reg.cuh);
+//   * one warp = 32 consecutive edges and is fully independent (no CTA barrier in the tile loop), weights are
+//     shared-memory resident and read at warp-uniform addresses;
+//   * the per-target aggregation is a warp-local segmented sum; pieces of segments that straddle 32-edge tiles
+//     are combined in tile order by a small fix-up kernel (deterministic, no atomics, no memset of the output);
+//   * backward recomputes each GVP from its stage input, stages the operands of the weight-gradient GEMMs in a
+//     warp-private shared-memory buffer and accumulates them in a warp-private arena.
+#include "cgvp_warp.cuh"
+
+using namespace cgvpr;
+
+#define CR_WARPS 8
+#define CR_THREADS (CR_WARPS * 32)
+
+struct ConvRegArgs {
+    long long E, N;
+    int ntiles, mean, edge_sorted, acc_edge;
+    const int *perm, *src, *dst, *rowptr;
+    const float *x_s, *x_v, *e_s, *e_v;
+    const float* wp[3];
+    float *out_s, *out_v;                 // forward output / backward: target-side node gradient
+    float *part_head, *part_tail;
+    const float *d_out_s, *d_out_v;
+    float *d_e_s, *d_e_v, *dj;
+    float* partial;                       // [gridDim.x][PF] weight-gradient partials
+};
+
+template <int NS_, int NV_, int ES_, int EV_, class G0_, class G1_, class G2_>
+struct ConvSpec {
+    static constexpr int NS = NS_, NV = NV_, ES = ES_, EV = EV_;
+    using G0 = G0_; using G1 = G1_; using G2 = G2_;
+    static_assert(G0::SI == 2 * NS + ES && G0::VI == 2 * NV + EV, "message input dims");
+    static_assert(G1::SI == G0::SO && G1::VI == G0::VO && G2::SI == G1::SO && G2::VI == G1::VO, "chain dims");
+    static_assert(G2::SO == NS && G2::VO == NV, "specialised conv maps node dims to node dims");
+    static constexpr int SO = G2::SO, VO = G2::VO;
+    static constexpr int CH = SO + 3 * VO;        // message channels = output node row
+    static constexpr int CHX = NS + 3 * NV;       // node row (gradient slices)
+    // shared-memory weight offsets (floats)
+    static constexpr int WF0 = 0, WF1 = G0::FWD_FLOATS, WF2 = WF1 + G1::FWD_FLOATS, WF = WF2 + G2::FWD_FLOATS;
+    static constexpr int WT0 = 0, WT1 = G0::TOTAL_FLOATS, WT2 = WT1 + G1::TOTAL_FLOATS, WT = WT2 + G2::TOTAL_FLOATS;
+    // gradient arena (= concatenated forward packed blocks)
+    static constexpr int GO0 = 0, GO1 = G0::FWD_FLOATS, GO2 = GO1 + G1::FWD_FLOATS, PF = GO2 + G2::FWD_FLOATS;
+    static constexpr int STG_COLS = imax(imax(sink_cols<G0>(), sink_cols<G1>()), sink_cols<G2>());
+    static constexpr int STG_FLOATS = imax(STG_COLS * CGVP_WPITCH * 4, pad4(imax(CH, CHX) * CGVP_WPITCH));
+    static constexpr size_t smem_fwd() { return (size_t)WF * 4 + (size_t)CR_WARPS * (CH * CGVP_WPITCH + 32) * 4; }
+    static constexpr size_t smem_bwd() { return (size_t)WT * 4 + (size_t)CR_WARPS * (PF + STG_FLOATS + 32) * 4; }
+    static bool matches(const CgvpConvDesc& d) {
+        return d.ns == NS && d.nv == NV && d.es == ES && d.ev == EV && d.n_gvp == 3 && G0::matches(d.gvp[0]) &&
+               G1::matches(d.gvp[1]) && G2::matches(d.gvp[2]);
+    }
+};
+
+__device__ __forceinline__ void copy_f4w(float* dst, const float* __restrict__ src, int nfloats) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+// message input (s_j, e_s, s_i), (V_j, e_V, V_i)  -- gvp_layers.py:306
+template <class S>
+__device__ __forceinline__ void load_message_input(const ConvRegArgs& a, int src, int dst, long long eid,
+                                                   float (&s0)[1][S::G0::SI], float (&v0)[3][S::G0::VI1]) {
+    load_s<S::NS, 0>(a.x_s, src, s0);
+    load_s<S::ES, S::NS>(a.e_s, eid, s0);
+    load_s<S::NS, S::NS + S::ES>(a.x_s, dst, s0);
+    load_v<S::NV, 0>(a.x_v, src, v0);
+    load_v<S::EV, S::NV>(a.e_v, eid, v0);
+    load_v<S::NV, S::NV + S::EV>(a.x_v, dst, v0);
+}
+
+template <class S>
+__global__ void __launch_bounds__(CR_THREADS, 2) conv_fwd_reg_kernel(const __grid_constant__ ConvRegArgs a) {
+    using G0 = typename S::G0; using G1 = typename S::G1; using G2 = typename S::G2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* wsm = reinterpret_cast<float*>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* M = wsm + S::WF + warp * (S::CH * CGVP_WPITCH + 32);
+    int* dsts = reinterpret_cast<int*>(M + S::CH * CGVP_WPITCH);
+    copy_f4w(wsm + S::WF0, a.wp[0], G0::FWD_FLOATS);
+    copy_f4w(wsm + S::WF1, a.wp[1], G1::FWD_FLOATS);
+    copy_f4w(wsm + S::WF2, a.wp[2], G2::FWD_FLOATS);
+    __syncthreads();
+    const int nw = gridDim.x * CR_WARPS;
+    for (int t = blockIdx.x * CR_WARPS + warp; t < a.ntiles; t += nw) {
+        const long long p0 = (long long)t * 32;
+        const int rv = (int)min(32LL, a.E - p0);
+        const long long p = lane < rv ? p0 + lane : p0;          // idle lanes replay the first row (never stored)
+        const int src = __ldg(a.src + p), dst = __ldg(a.dst + p);
+        const long long eid = a.edge_sorted ? p : (long long)__ldg(a.perm + p);
+        float s1[1][G0::SO], v1[3][G0::VO1];
+        {
+            float s0[1][G0::SI], v0[3][G0::VI1];
+            load_message_input<S>(a, src, dst, eid, s0, v0);
+            Save<G0> sv;
+            gvp_fwd<G0>(wsm + S::WF0, s0, v0, s1, v1, sv);
+        }
+        float s2[1][G1::SO], v2[3][G1::VO1];
+        { Save<G1> sv; gvp_fwd<G1>(wsm + S::WF1, s1, v1, s2, v2, sv); }
+        float s3[1][G2::SO], v3[3][G2::VO1];
+        { Save<G2> sv; gvp_fwd<G2>(wsm + S::WF2, s2, v2, s3, v3, sv); }
+#pragma unroll
+        for (int c = 0; c < S::SO; ++c) M[c * CGVP_WPITCH + lane] = s3[0][c];
+#pragma unroll
+        for (int c = 0; c < S::VO; ++c)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) M[(S::SO + 3 * c + q) * CGVP_WPITCH + lane] = v3[q][c];
+        dsts[lane] = dst;
+        __syncwarp();
+        seg_reduce_warp<S::CH, S::SO>(M, dsts, lane, rv, p0, t, a.rowptr, a.mean != 0, a.out_s, a.out_v, a.part_head, a.part_tail);
+        __syncwarp();
+    }
+}
+
+// Nodes whose segment straddles 32-edge tiles (pieces summed in tile order) and nodes without incoming edges (zero,
+// PyG scatter with dim_size = N).  All other nodes were written by the main kernel.
+__global__ void conv_fixup_kernel(long long N, int CH, int SW, const int* __restrict__ rowptr, int mean,
+                                  const float* __restrict__ part_head, const float* __restrict__ part_tail,
+                                  float* __restrict__ out_s, float* __restrict__ out_v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * CH) return;
+    const long long n = i / CH;
+    const int ch = (int)(i - n * CH);
+    const long long a = rowptr[n], b = rowptr[n + 1];
+    float val;
+    if (b <= a) {
+        val = 0.f;
+    } else {
+        const long long ta = a >> 5, tb = (b - 1) >> 5;
+        if (ta == tb) return;
+        float sum = part_tail[ta * CH + ch];
+        for (long long t = ta + 1; t <= tb; ++t) sum += part_head[t * CH + ch];
+        val = mean ? sum / (float)max((int)(b - a), 1) : sum;
+    }
+    if (ch < SW) out_s[n * SW + ch] = val;
+    else out_v[n * (CH - SW) + (ch - SW)] = val;
+}
+
+template <class S>
+__global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __grid_constant__ ConvRegArgs a) {
+    using G0 = typename S::G0; using G1 = typename S::G1; using G2 = typename S::G2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* wsm = reinterpret_cast<float*>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* arena0 = wsm + S::WT;
+    float* arena = arena0 + warp * (S::PF + S::STG_FLOATS + 32);
+    float* stgf = arena + S::PF;
+    int* dsts = reinterpret_cast<int*>(stgf + S::STG_FLOATS);
+    copy_f4w(wsm + S::WT0, a.wp[0], G0::TOTAL_FLOATS);
+    copy_f4w(wsm + S::WT1, a.wp[1], G1::TOTAL_FLOATS);
+    copy_f4w(wsm + S::WT2, a.wp[2], G2::TOTAL_FLOATS);
+    for (int i = lane; i < S::PF; i += 32) arena[i] = 0.f;
+    __syncthreads();
+    const int nw = gridDim.x * CR_WARPS;
+    for (int t = blockIdx.x * CR_WARPS + warp; t < a.ntiles; t += nw) {
+        const long long p0 = (long long)t * 32;
+        const int rv = (int)min(32LL, a.E - p0);
+        const bool valid = lane < rv;
+        const long long p = valid ? p0 + lane : p0;
+        const int src = __ldg(a.src + p), dst = __ldg(a.dst + p);
+        const long long eid = a.edge_sorted ? p : (long long)__ldg(a.perm + p);
+        WarpSink sink{reinterpret_cast<float4*>(stgf), arena, lane, valid};
+        // forward chain, keeping only the stage inputs (each GVP is recomputed right before its backward)
+        float s1[1][G0::SO], v1[3][G0::VO1], s2[1][G1::SO], v2[3][G1::VO1];
+        {
+            float s0[1][G0::SI], v0[3][G0::VI1];
+            load_message_input<S>(a, src, dst, eid, s0, v0);
+            Save<G0> sv;
+            gvp_fwd<G0>(wsm + S::WT0, s0, v0, s1, v1, sv);
+        }
+        { Save<G1> sv; gvp_fwd<G1>(wsm + S::WT1, s1, v1, s2, v2, sv); }
+        // d(message_e) = d_out[dst_e] (/ deg for mean)
+        float gs3[1][S::SO], gv3[3][G2::VO1];
+        load_s<S::SO, 0>(a.d_out_s, dst, gs3);
+        load_v<S::VO, 0>(a.d_out_v, dst, gv3);
+        if (a.mean) {
+            const float f = 1.f / (float)max(__ldg(a.rowptr + dst + 1) - __ldg(a.rowptr + dst), 1);
+#pragma unroll
+            for (int c = 0; c < S::SO; ++c) gs3[0][c] *= f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int c = 0; c < S::VO; ++c) gv3[q][c] *= f;
+        }
+        float gs2[1][G1::SO], gv2[3][G1::VO1];
+        {
+            Save<G2> sv;
+            float so[1][G2::SO], vo[3][G2::VO1], dsin[1][G2::KSD], dvin[3][G2::VI1];
+            gvp_fwd<G2>(wsm + S::WT2, s2, v2, so, vo, sv);
+            gvp_bwd<G2>(wsm + S::WT2, sv, s2, v2, gs3, gv3, sink, S::GO2, dsin, dvin);
+#pragma unroll
+            for (int c = 0; c < G2::SI; ++c) gs2[0][c] = dsin[0][c];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int c = 0; c < G2::VI; ++c) gv2[q][c] = dvin[q][c];
+        }
+        float gs1[1][G0::SO], gv1[3][G0::VO1];
+        {
+            Save<G1> sv;
+            float so[1][G1::SO], vo[3][G1::VO1], dsin[1][G1::KSD], dvin[3][G1::VI1];
+            gvp_fwd<G1>(wsm + S::WT1, s1, v1, so, vo, sv);
+            gvp_bwd<G1>(wsm + S::WT1, sv, s1, v1, gs2, gv2, sink, S::GO1, dsin, dvin);
+#pragma unroll
+            for (int c = 0; c < G1::SI; ++c) gs1[0][c] = dsin[0][c];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int c = 0; c < G1::VI; ++c) gv1[q][c] = dvin[q][c];
+        }
+        float dsin[1][G0::KSD], dvin[3][G0::VI1];
+        {
+            float s0[1][G0::SI], v0[3][G0::VI1];
+            load_message_input<S>(a, src, dst, eid, s0, v0);
+            Save<G0> sv;
+            float so[1][G0::SO], vo[3][G0::VO1];
+            gvp_fwd<G0>(wsm + S::WT0, s0, v0, so, vo, sv);
+            gvp_bwd<G0>(wsm + S::WT0, sv, s0, v0, gs1, gv1, sink, S::GO0, dsin, dvin);
+        }
+        if (valid) {
+            // edge-attribute gradient (one row per edge, written or accumulated)
+            if (a.d_e_s) store_s<S::ES, S::NS>(a.d_e_s, eid, dsin, a.acc_edge != 0);
+            if (a.d_e_v) store_v<S::EV, S::NV>(a.d_e_v, eid, dvin, a.acc_edge != 0);
+            // source-side slice, one merged row per edge (reduced over the source CSR view afterwards)
+            float dj[1][S::CHX];
+#pragma unroll
+            for (int c = 0; c < S::NS; ++c) dj[0][c] = dsin[0][c];
+#pragma unroll
+            for (int c = 0; c < S::NV; ++c)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) dj[0][S::NS + 3 * c + q] = dvin[q][c];
+            store_s<S::CHX, 0>(a.dj, p, dj, false);
+        }
+        // target-side slice: segmented sum over the target node
+        float* M = stgf;
+#pragma unroll
+        for (int c = 0; c < S::NS; ++c) M[c * CGVP_WPITCH + lane] = dsin[0][S::NS + S::ES + c];
+#pragma unroll
+        for (int c = 0; c < S::NV; ++c)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) M[(S::NS + 3 * c + q) * CGVP_WPITCH + lane] = dvin[q][S::NV + S::EV + c];
+        dsts[lane] = dst;
+        __syncwarp();
+        seg_reduce_warp<S::CHX, S::NS>(M, dsts, lane, rv, p0, t, a.rowptr, false, a.out_s, a.out_v, a.part_head, a.part_tail);
+        __syncwarp();
+    }
+    // CTA partial = sum of the warps' arenas in warp order (deterministic)
+    __syncthreads();
+    float* out = a.partial + (long long)blockIdx.x * S::PF;
+    for (int i = threadIdx.x; i < S::PF; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < CR_WARPS; ++w) sum += arena0[w * (S::PF + S::STG_FLOATS + 32) + i];
+        out[i] = sum;
+    }
+}
+
+// ---- instances --------------------------------------------------------------------------------------------------
+// CASTER-DTA checkpoint dims: nodes (16,4), edges (32,1), message GVPs with (ReLU, None) activations and vector gate
+// (models/protein_gnn.py:341-349, pretrained_model_downstream/model_kwargs.json).
+using CkG0 = GvpC<64, 9, 16, 4, 9, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
+using CkG1 = GvpC<16, 4, 16, 4, 4, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
+using CkG2 = GvpC<16, 4, 16, 4, 4, CGVP_ACT_NONE, CGVP_ACT_NONE, 1>;
+using ConvCk = ConvSpec<16, 4, 32, 1, CkG0, CkG1, CkG2>;
+
+static bool g_fast_paths = true;
+extern "C" int32_t cgvp_set_fast_paths(int32_t on) { g_fast_paths = on != 0; return 0; }
+bool cgvp_fast_paths_enabled() { return g_fast_paths; }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <class S>
+static void fill_common(ConvRegArgs& a, const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
+                        const float* e_s, const float* e_v, const float* const* h_packed) {
+    memset(&a, 0, sizeof(a));
+    a.E = plan->num_edges; a.N = plan->num_nodes;
+    a.ntiles = (int)cdiv64(a.E, 32);
+    a.mean = desc->aggr == CGVP_AGGR_MEAN; a.edge_sorted = desc->edge_sorted;
+    a.perm = plan->perm; a.src = plan->src; a.dst = plan->dst; a.rowptr = plan->rowptr;
+    a.x_s = x_s; a.x_v = x_v; a.e_s = e_s; a.e_v = e_v;
+    for (int k = 0; k < 3; ++k) a.wp[k] = h_packed[k];
+}
+
+// Returns 1 if this descriptor / these buffers are served by a specialised kernel (rc_out holds the result), else 0.
+int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
+                     const float* e_v, const float* const* h_packed, float* out_s, float* out_v, float* part_head,
+                     float* part_tail, cudaStream_t st, int* rc_out) {
+    using S = ConvCk;
+    if (!g_fast_paths || !S::matches(*desc) || plan->num_edges <= 0 || plan->num_nodes <= 0) return 0;
+    if (!(aligned16(x_s) && aligned16(x_v) && aligned16(e_s) && aligned16(out_s) && aligned16(out_v))) return 0;
+    ConvRegArgs a;
+    fill_common<S>(a, desc, plan, x_s, x_v, e_s, e_v, h_packed);
+    a.out_s = out_s; a.out_v = out_v; a.part_head = part_head; a.part_tail = part_tail;
+    *rc_out = 0;
+    const int sms = cgvp_num_sms();
+    const int grid = (int)min((long long)cdiv(a.ntiles, CR_WARPS), (long long)sms * 2);
+    const size_t smem = S::smem_fwd();
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_reg_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cgvp_set_error("conv_fwd_reg: %s", cudaGetErrorString(e)); *rc_out = (int)e; return 1; }
+    cgvp_prof_begin(CGVP_K_CONV_FWD, st);
+    conv_fwd_reg_kernel<S><<<grid, CR_THREADS, smem, st>>>(a);
+    cgvp_prof_end(CGVP_K_CONV_FWD, st);
+    const long long tot = a.N * S::CH;
+    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CH, S::SO, a.rowptr, a.mean, part_head, part_tail, out_s, out_v);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cgvp_set_error("launch of conv_fwd_reg_kernel failed: %s", cudaGetErrorString(e)); *rc_out = (int)e; }
+    return 1;
+}
+
+int conv_bwd_special_partial_floats(const CgvpConvDesc* desc) { return ConvCk::matches(*desc) ? ConvCk::PF : 0; }
+
+// d_x_* receive the TARGET-side gradient here; the caller adds the source side (segment reduce of dj over the source
+// CSR view) and reduces the `grid_out` partials of `pf_out` floats each.
+int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
+                     const float* e_v, const float* const* h_packed, const float* d_out_s, const float* d_out_v,
+                     float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
+                     float* part_tail, float* dj, float* partial, int max_grid, cudaStream_t st, int* grid_out, int* rc_out) {
+    using S = ConvCk;
+    if (!g_fast_paths || !S::matches(*desc) || plan->num_edges <= 0 || plan->num_nodes <= 0) return 0;
+    if (!(aligned16(x_s) && aligned16(x_v) && aligned16(e_s) && aligned16(d_out_s) && aligned16(d_out_v) && aligned16(d_x_s) &&
+          aligned16(d_x_v) && aligned16(dj) && (!d_e_s || aligned16(d_e_s))))
+        return 0;
+    ConvRegArgs a;
+    fill_common<S>(a, desc, plan, x_s, x_v, e_s, e_v, h_packed);
+    a.out_s = d_x_s; a.out_v = d_x_v; a.part_head = part_head; a.part_tail = part_tail;
+    a.d_out_s = d_out_s; a.d_out_v = d_out_v; a.d_e_s = d_e_s; a.d_e_v = d_e_v; a.dj = dj; a.acc_edge = accumulate_edge;
+    a.partial = partial;
+    *rc_out = 0;
+    const int sms = cgvp_num_sms();
+    int grid = (int)min((long long)cdiv(a.ntiles, CR_WARPS), (long long)sms);
+    if (grid > max_grid) grid = max_grid;
+    *grid_out = grid;
+    const size_t smem = S::smem_bwd();
+    cudaError_t e = cudaFuncSetAttribute(conv_bwd_reg_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cgvp_set_error("conv_bwd_reg: %s", cudaGetErrorString(e)); *rc_out = (int)e; return 1; }
+    cgvp_prof_begin(CGVP_K_CONV_BWD, st);
+    conv_bwd_reg_kernel<S><<<grid, CR_THREADS, smem, st>>>(a);
+    cgvp_prof_end(CGVP_K_CONV_BWD, st);
+    const long long tot = a.N * S::CHX;
+    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CHX, S::NS, a.rowptr, 0, part_head, part_tail, d_x_s, d_x_v);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cgvp_set_error("launch of conv_bwd_reg_kernel failed: %s", cudaGetErrorString(e)); *rc_out = (int)e; }
+    return 1;
+}

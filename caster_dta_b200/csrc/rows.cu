@@ -6,6 +6,11 @@
 
 using namespace cgvp;
 
+int rows_fwd_special(const CgvpRowDesc* desc, const CgvpRowArgs* args, cudaStream_t st, int* rc);
+int rows_bwd_special(const CgvpRowDesc* desc, const CgvpRowArgs* args, const CgvpRowGradArgs* grads, void* ws, int64_t ws_bytes,
+                     cudaStream_t st, int* rc);
+int rows_special_partial_floats(const CgvpRowDesc* desc);
+
 struct RowsK {
     int in_s, in_v, onehot, has_res, pre_norm, n_gvp, post_res, post_norm;
     int s0, so_last, vo_last;            // scalar width of stage 0 (onehot + in_s); output dims
@@ -410,7 +415,8 @@ extern "C" int64_t cgvp_rows_workspace_bytes(const CgvpRowDesc* desc, int64_t ro
     RowsK K;
     if (build_rows_k(desc, true, K)) return -1;
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
-    return (int64_t)(2 * sms + 1) * K.partial_floats * 4 + 256;
+    const int pf = imax(K.partial_floats, rows_special_partial_floats(desc));
+    return (int64_t)(2 * sms + 1) * pf * 4 + 256;
 }
 
 static int check_args(const RowsK& K, const CgvpRowArgs* a) {
@@ -433,6 +439,10 @@ extern "C" int32_t cgvp_rows_fwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
     if (check_args(K, args)) return -1;
     CGVP_REQUIRE(args->out_s && (K.vo_last == 0 || args->out_v), "rows: null output");
     if (args->rows == 0) return 0;
+    {   // register-resident specialised kernels for the dims they were compiled for (rows_reg.cu)
+        int rc = 0;
+        if (rows_fwd_special(desc, args, (cudaStream_t)stream, &rc)) return rc;
+    }
     size_t smem = 0;
     if (choose_geometry(K, cgvp_max_smem_optin(), &smem)) return -1;
     K.a = *args;
@@ -466,6 +476,10 @@ extern "C" int32_t cgvp_rows_bwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
     CGVP_REQUIRE(K.n_gvp == 0 || grads->h_packed_grads, "rows_bwd: packed gradient blocks missing");
     CGVP_REQUIRE(!K.has_res || !grads->d_h_s || K.in_v == 0 || grads->d_h_v, "rows_bwd: d_h_v missing");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int rc = 0;
+        if (rows_bwd_special(desc, args, grads, ws, ws_bytes, st, &rc)) return rc;
+    }
     size_t smem = 0;
     if (choose_geometry(K, cgvp_max_smem_optin(), &smem)) return -1;
     K.a = *args;

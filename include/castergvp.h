@@ -57,6 +57,13 @@ const char* cgvp_last_error(void);
 int32_t cgvp_version(void);
 int32_t cgvp_sm_count(void); /* SMs of the current device (grid sizing), 0 if no device */
 
+/* ---- kernel selection (testing / measurement aid; no reference counterpart) -----------------------------------
+ * Descriptors whose dims match a compiled-in specialisation (the CASTER-DTA checkpoint dims: message chain of
+ * GVPConv on (16,4)/(32,1), gvp_node, gvp_edge, node update, readout) are served by register-resident kernels
+ * (csrc/conv_reg.cu, csrc/rows_reg.cu); everything else by the generic shared-memory tile kernels.  Passing 0
+ * forces the generic kernels (parity tests compare the two).  Default 1. */
+int32_t cgvp_set_fast_paths(int32_t on);
+
 /* ---- kernel timing (measurement aid; no reference counterpart) ------------------------------------------------
  * When enabled, the library brackets the MAIN kernel of each operator with cudaEvents on the caller's stream.
  * cgvp_profile_collect synchronises on the recorded events and returns the summed device time and the launch

@@ -21,6 +21,16 @@ def _mods():
     return cg
 
 
+@pytest.fixture(params=["fast", "generic"])
+def kernel_path(request):
+    """Run a test once with the specialised register-resident kernels (where compiled in) and once with the
+    generic tile kernels only (`cgvp_set_fast_paths`)."""
+    from caster_dta_b200 import _lib
+    _lib.set_fast_paths(request.param == "fast")
+    yield request.param
+    _lib.set_fast_paths(True)
+
+
 def _act(name):
     import torch.nn.functional as F
     return {None: None, "relu": F.relu, "sigmoid": torch.sigmoid}[name]
@@ -143,7 +153,7 @@ def test_gvp_conv_layer_golden(name):
 
 
 @pytest.mark.parametrize("name", ["radius4", "knn10"])
-def test_lba_encoder_checkpoint_golden(name):
+def test_lba_encoder_checkpoint_golden(name, kernel_path):
     """Protein slice of the shipped checkpoint, loaded with strict=True, reproduces the reference embeddings."""
     cg = _mods()
     g = golden("lba_checkpoint")
@@ -239,7 +249,7 @@ def _random_layer_case(n, e, nd, ed, seed, hub=False, aggr="sum"):
     (257, 3000, (10, 3), (7, 2), True, "sum"),
     (64, 0, (16, 4), (32, 1), False, "sum"),
 ])
-def test_conv_layer_vs_oracle(n, e, nd, ed, hub, aggr):
+def test_conv_layer_vs_oracle(n, e, nd, ed, hub, aggr, kernel_path):
     cg = _mods()
     from oracle import gvp_oracle
     import torch.nn.functional as F
@@ -264,6 +274,45 @@ def test_conv_layer_vs_oracle(n, e, nd, ed, hub, aggr):
     for name, prm in m.named_parameters():
         if prm.numel() and p64[name].grad is not None:
             assert_close(prm.grad, p64[name].grad, TOL, "grad " + name, atol=1e-5)
+
+
+def test_fast_and_generic_kernels_agree_in_training_mode():
+    """LBA encoder at checkpoint dims, train mode with dropout (masks drawn from the same seeded torch RNG stream),
+    ragged kNN-like in-degrees and a tail tile: the register-resident kernels and the generic tile kernels must
+    agree on the embedding and on every gradient to fp32 round-off."""
+    cg = _mods()
+    from caster_dta_b200 import _lib
+    kw = dict(base_conv="lbamodel", in_channels=[17, 3], edge_dim=[32, 1], num_ntypes=20, num_etypes=1,
+              ntype_emb_dim=None, etype_emb_dim=None, num_convs=2, hidden_channels=[16, 4],
+              edge_hidden_channels=[32, 1], out_channels=64, dropout_rate=0.2, activation="leaky_relu", aggr="mean")
+    torch.manual_seed(3)
+    enc = cg.SelectableProteinModelWrapper(**kw).to(DEV).train()
+    g = torch.Generator().manual_seed(4)
+    n, e = 1237, 30011
+    src, dst = torch.randint(0, n, (e,), generator=g), torch.randint(0, n, (e,), generator=g)
+    dst[:200] = 5
+    ei = torch.stack([src, dst]).to(DEV)
+    xs, xv = torch.randn(n, 17, generator=g), torch.randn(n, 3, 3, generator=g)
+    es, ev = torch.randn(e, 32, generator=g), torch.randn(e, 1, 3, generator=g)
+    nt, et = torch.randint(0, 20, (n,), generator=g).to(DEV), torch.zeros(e, dtype=torch.long, device=DEV)
+    cot = torch.randn(n, 64, generator=g).to(DEV)
+    res = {}
+    for mode in (True, False):
+        _lib.set_fast_paths(mode)
+        try:
+            torch.manual_seed(11)
+            a, b, c, d = _leaf(xs), _leaf(xv), _leaf(es), _leaf(ev)
+            enc.zero_grad(set_to_none=True)
+            out = enc((a, b), ei, nt, et, eattr=(c, d))
+            (out * cot).sum().backward()
+            res[mode] = (out.detach(), a.grad, b.grad, c.grad, d.grad, {k: p.grad.clone() for k, p in enc.named_parameters() if p.numel()})
+        finally:
+            _lib.set_fast_paths(True)
+    f, gnr = res[True], res[False]
+    for i, what in enumerate(("embedding", "grad_x_s", "grad_x_v", "grad_e_s", "grad_e_v")):
+        assert_close(f[i], gnr[i].cpu(), TIGHT, what, atol=1e-6)
+    for k in f[5]:
+        assert_close(f[5][k], gnr[5][k].cpu(), TIGHT, "grad " + k, atol=1e-5)
 
 
 def test_conv_is_bit_reproducible_and_order_invariant():
