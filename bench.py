@@ -286,6 +286,25 @@ def main():
     dominant = max(("conv_fwd", "conv_bwd", "rows_fwd", "rows_bwd", "segment_reduce"), key=lambda k: prof[k][0])
     _lib.profile_enable(False)
 
+    if os.environ.get("CGVP_BENCH_TRACE") and rank == 0:      # diagnostics only: where does a step spend CPU / GPU time
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as tp:
+            for _ in range(3):
+                step(resident)
+            torch.cuda.synchronize()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "step_trace.txt"), "w") as fh:
+            fh.write(tp.key_averages().table(sort_by="self_cpu_time_total", row_limit=45))
+            fh.write("\n\n")
+            fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=45))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step(resident)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"[trace] 5 steps: cpu issue {1e3 * (t1 - t0) / 5:.2f} ms/step, incl. drain {1e3 * (t2 - t0) / 5:.2f} ms/step", file=sys.stderr)
+
     # ---- timed region 1: device-resident inputs ------------------------------------------------------------------------
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     clocks = ClockSampler(local)
