@@ -1,0 +1,30 @@
+"""CUDA-graph capture of a fixed-shape step (forward + backward) of the accelerated model.
+
+After the GVP stack is fused, a CASTER-DTA training step is ~500 small launches and CPU-launch-bound; replaying it as
+one CUDA graph makes it GPU-bound.  Every C-ABI entry point is capture-safe (no allocation, no synchronisation, all
+work on the caller's stream), torch's caching allocator serves the workspaces from the graph's private pool, and the
+dropout masks keep following torch's (graph-aware) Philox stream.
+
+Usage: shapes must be fixed -- copy each batch into the `static` tensors the step closes over, then `replay()`.
+"""
+import torch
+
+
+class GraphedStep:
+    def __init__(self, fn, warmup=3):
+        """`fn()` runs one step on static input tensors and returns a tensor (e.g. the loss)."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.out

@@ -75,11 +75,16 @@ class HomoMoleculeGNN_GINE(nn.Module):
             for i in range(num_convs))
 
     def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
-        x = torch.cat([F.one_hot(ntypes, self.num_ntypes).to(x.dtype), x], -1)
-        e = torch.cat([F.one_hot(etypes, self.num_etypes).to(x.dtype), eattr], -1)
+        x = torch.cat([_one_hot(ntypes, self.num_ntypes, x.dtype), x], -1)
+        e = torch.cat([_one_hot(etypes, self.num_etypes, x.dtype), eattr], -1)
         for conv in self.conv_list[:-1]:
             x = self.dropout(self.activation(conv(x, edge_index, e)))
         return self.activation(self.conv_list[-1](x, edge_index, e))
+
+
+def _one_hot(idx, num_classes, dtype):
+    """`F.one_hot` without its device->host range check (a sync, and illegal during CUDA-graph capture)."""
+    return (idx.unsqueeze(-1) == torch.arange(num_classes, device=idx.device)).to(dtype)
 
 
 class SelectableMoleculeModelWrapper(nn.Module):
@@ -104,14 +109,13 @@ def to_dense_batch(x, batch, num_graphs=None, max_nodes=None):
     if batch is None:
         return x.unsqueeze(0), torch.ones(1, x.shape[0], dtype=torch.bool, device=x.device)
     b = int(batch[-1]) + 1 if num_graphs is None else int(num_graphs)
-    counts = torch.bincount(batch, minlength=b)
+    counts = torch.zeros(b, dtype=torch.long, device=x.device).index_add_(0, batch, torch.ones_like(batch))   # bincount syncs
     start = torch.cumsum(counts, 0) - counts
     m = int(counts.max()) if max_nodes is None else int(max_nodes)
     pos = torch.arange(x.shape[0], device=x.device) - start[batch]
     out = x.new_zeros((b, m, x.shape[1]))
     out[batch, pos] = x
-    mask = torch.zeros(b, m, dtype=torch.bool, device=x.device)
-    mask[batch, pos] = True
+    mask = torch.arange(m, device=x.device).unsqueeze(0) < counts.unsqueeze(1)      # [B, max]: row r of graph g is real
     return out, mask
 
 

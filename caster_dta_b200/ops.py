@@ -213,11 +213,12 @@ class RowsFunction(torch.autograd.Function):
         t["out_v"] = torch.empty(rows, prog.out_v, 3, dtype=torch.float32, device=dev)
         a, blocks = _row_args(prog, rows, t, arena, offs)
         _lib.timed_call("cgvp_rows_fwd", lib().cgvp_rows_fwd, C.byref(prog.desc), C.byref(a), None, 0, _stream())
+        out_s, out_v = t.pop("out_s"), t.pop("out_v")     # never keep the outputs on ctx: node -> output -> node leaks
         ctx.prog, ctx.t, ctx.arena, ctx.offs, ctx.rows = prog, t, arena, offs, rows
         ctx.weights = weights
         ctx.in_rows = int(in_s.shape[0])
-        ctx.mark_non_differentiable(*([] if prog.out_v else [t["out_v"]]))
-        return t["out_s"], t["out_v"]
+        ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
+        return out_s, out_v
 
     @staticmethod
     def backward(ctx, d_out_s, d_out_v):
