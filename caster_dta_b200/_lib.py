@@ -65,6 +65,7 @@ SIGNATURES = {
     "cgvp_version": (C.c_int32, []),
     "cgvp_sm_count": (C.c_int32, []),
     "cgvp_set_fast_paths": (C.c_int32, [C.c_int32]),
+    "cgvp_set_tensor_cores": (C.c_int32, [C.c_int32]),
     "cgvp_profile_enable": (C.c_int32, [C.c_int32]),
     "cgvp_profile_collect": (C.c_int32, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cgvp_gvp_packed_floats": (C.c_int64, [C.POINTER(GvpDesc)]),
@@ -104,6 +105,11 @@ KERNEL_IDS = {"conv_fwd": 0, "conv_bwd": 1, "rows_fwd": 2, "rows_bwd": 3, "segme
 def set_fast_paths(on):
     """1 (default): specialised register-resident kernels where compiled in; 0: generic tile kernels only."""
     lib().cgvp_set_fast_paths(int(bool(on)))
+
+
+def set_tensor_cores(on):
+    """0 (default): fp32 everywhere; 1: tcgen05 bf16 message GEMMs where compiled in (<= 1e-2 of the reference)."""
+    lib().cgvp_set_tensor_cores(int(bool(on)))
 
 
 def profile_enable(on):

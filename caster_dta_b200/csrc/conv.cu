@@ -13,6 +13,11 @@ int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float
                      float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
                      float* part_tail, float* dj, float* partial, int max_grid, cudaStream_t st, int* grid_out, int* rc_out);
 
+int64_t conv_tc_workspace_bytes(const CgvpConvDesc* desc, int64_t E, int64_t N);
+int conv_fwd_tc(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
+                const float* e_v, const float* const* h_packed, float* out_s, float* out_v, void* tcws, int64_t tcws_bytes,
+                cudaStream_t st, int* rc_out);
+
 int cgvp_segment_reduce_split(const float* rows, int width, const int* rowptr, const int* index, int64_t N, int aggr,
                               int beta, float* out_a, int wa, float* out_b, int wb, cudaStream_t st);
 
@@ -420,7 +425,9 @@ extern "C" int64_t cgvp_conv_workspace_bytes(const CgvpConvDesc* desc, int64_t n
     if (build_conv_k(desc, backward != 0, K)) return -1;
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
     int64_t a, b, c, d, e, f;
-    return conv_ws_layout(K, num_edges, num_nodes, backward != 0, 4 * sms, &a, &b, &c, &d, &e, &f);
+    // the tensor-core forward (conv_tc.cu) keeps its own region after the common layout
+    return conv_ws_layout(K, num_edges, num_nodes, backward != 0, 4 * sms, &a, &b, &c, &d, &e, &f) +
+           (backward ? 0 : conv_tc_workspace_bytes(desc, num_edges, num_nodes));
 }
 
 static int conv_common_checks(const ConvK& K, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
@@ -445,12 +452,13 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
     CGVP_REQUIRE(out_s && (K.vo == 0 || out_v), "conv_fwd: null output");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = plan->num_edges, N = plan->num_nodes;
-    if (E > 0 && N > 0) {   // register-resident specialised kernel for the dims it was compiled for (conv_reg.cu)
+    if (E > 0 && N > 0) {   // specialised kernels for the dims they were compiled for (conv_tc.cu, conv_reg.cu)
         int64_t oh, ot, oc, od, op, orr;
-        const int64_t need = conv_ws_layout(K, E, N, false, 1, &oh, &ot, &oc, &od, &op, &orr);
+        const int64_t need = conv_ws_layout(K, E, N, false, 4 * (cgvp_num_sms() > 0 ? cgvp_num_sms() : 148), &oh, &ot, &oc, &od, &op, &orr);
         if (ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0) {
             char* base = reinterpret_cast<char*>(ws);
             int rc = 0;
+            if (conv_fwd_tc(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, base + need, ws_bytes - need, st, &rc)) return rc;
             if (conv_fwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, reinterpret_cast<float*>(base + oh),
                                  reinterpret_cast<float*>(base + ot), st, &rc))
                 return rc;

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(CR_THREADS, 2) conv_fwd_reg_kernel(const __gri
 
 // Nodes whose segment straddles 32-edge tiles (pieces summed in tile order) and nodes without incoming edges (zero,
 // PyG scatter with dim_size = N).  All other nodes were written by the main kernel.
-__global__ void conv_fixup_kernel(long long N, int CH, int SW, const int* __restrict__ rowptr, int mean,
+__global__ void conv_fixup_kernel(long long N, int CH, int SW, const int* __restrict__ rowptr, int mean, int tile_shift,
                                   const float* __restrict__ part_head, const float* __restrict__ part_tail,
                                   float* __restrict__ out_s, float* __restrict__ out_v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,7 +127,7 @@ __global__ void conv_fixup_kernel(long long N, int CH, int SW, const int* __rest
     if (b <= a) {
         val = 0.f;
     } else {
-        const long long ta = a >> 5, tb = (b - 1) >> 5;
+        const long long ta = a >> tile_shift, tb = (b - 1) >> tile_shift;
         if (ta == tb) return;
         float sum = part_tail[ta * CH + ch];
         for (long long t = ta + 1; t <= tb; ++t) sum += part_head[t * CH + ch];
@@ -302,7 +302,7 @@ int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float
     conv_fwd_reg_kernel<S><<<grid, CR_THREADS, smem, st>>>(a);
     cgvp_prof_end(CGVP_K_CONV_FWD, st);
     const long long tot = a.N * S::CH;
-    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CH, S::SO, a.rowptr, a.mean, part_head, part_tail, out_s, out_v);
+    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CH, S::SO, a.rowptr, a.mean, 5, part_head, part_tail, out_s, out_v);
     e = cudaGetLastError();
     if (e != cudaSuccess) { cgvp_set_error("launch of conv_fwd_reg_kernel failed: %s", cudaGetErrorString(e)); *rc_out = (int)e; }
     return 1;
@@ -338,7 +338,7 @@ int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float
     conv_bwd_reg_kernel<S><<<grid, CR_THREADS, smem, st>>>(a);
     cgvp_prof_end(CGVP_K_CONV_BWD, st);
     const long long tot = a.N * S::CHX;
-    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CHX, S::NS, a.rowptr, 0, part_head, part_tail, d_x_s, d_x_v);
+    conv_fixup_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(a.N, S::CHX, S::NS, a.rowptr, 0, 5, part_head, part_tail, d_x_s, d_x_v);
     e = cudaGetLastError();
     if (e != cudaSuccess) { cgvp_set_error("launch of conv_bwd_reg_kernel failed: %s", cudaGetErrorString(e)); *rc_out = (int)e; }
     return 1;

@@ -95,40 +95,41 @@ extern "C" int32_t cgvp_plan_build(const int64_t* edge_index, const CgvpPlan* pl
 }
 
 // ---- gather of the message input (gvp_layers.py:303-306) ----------------------------------------------------------
-// One thread per output float4 (scalars) / float (vectors); writes are fully coalesced, reads are row segments.
-template <bool VEC4>
-__global__ void __launch_bounds__(256) gather_scalar_kernel(const int64_t* __restrict__ ei, int64_t E, int ns, int es,
-                                                            const float* __restrict__ s, const float* __restrict__ e_s,
-                                                            float* __restrict__ ms) {
-    constexpr int V = VEC4 ? 4 : 1;
-    const int w = (2 * ns + es) / V, nsv = ns / V, esv = es / V;
-    const int64_t total = E * w;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i / w;
-        const int c = (int)(i - e * w);
-        const float* src;
-        if (c < nsv) src = s + ei[e] * ns + c * V;
-        else if (c < nsv + esv) src = e_s + e * es + (c - nsv) * V;
-        else src = s + ei[E + e] * ns + (c - nsv - esv) * V;
-        if (VEC4) reinterpret_cast<float4*>(ms)[i] = __ldg(reinterpret_cast<const float4*>(src));
-        else ms[i] = __ldg(src);
+// A CTA of (columns per edge) x (edges per pass) threads: every thread owns ONE output column (a float4 of the scalar
+// row, or a float of the vector row) for its whole life, so which source tensor it reads, and at which offset, is
+// decided once; the edge loop is index load -> row load -> coalesced store with no division.
+template <class T>   // T = float4 (16-byte columns) or float
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restrict__ ei, int64_t E, int w_node, int w_edge,
+                                                          const T* __restrict__ node, const T* __restrict__ edge,
+                                                          T* __restrict__ out) {
+    const int w = 2 * w_node + w_edge;              // columns per output row
+    const int epp = blockDim.x / w;                 // edges per pass of this CTA
+    const int c = threadIdx.x % w, de = threadIdx.x / w;
+    if (de >= epp) return;
+    // 0: source row of `node`, 1: the edge's own row, 2: target row of `node`
+    const int kind = c < w_node ? 0 : (c < w_node + w_edge ? 1 : 2);
+    const int off = kind == 0 ? c : (kind == 1 ? c - w_node : c - w_node - w_edge);
+    const int64_t stride = (int64_t)gridDim.x * epp;
+    for (int64_t e = (int64_t)blockIdx.x * epp + de; e < E; e += stride) {
+        T v;
+        if (kind == 1) v = __ldg(edge + e * w_edge + off);
+        else v = __ldg(node + __ldg(ei + (kind == 0 ? e : E + e)) * w_node + off);
+        out[e * w + c] = v;
     }
 }
 
-__global__ void __launch_bounds__(256) gather_vector_kernel(const int64_t* __restrict__ ei, int64_t E, int nv, int ev,
-                                                            const float* __restrict__ v, const float* __restrict__ e_v,
-                                                            float* __restrict__ mv) {
-    const int w = 3 * (2 * nv + ev), nvw = 3 * nv, evw = 3 * ev;
-    const int64_t total = E * w;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i / w;
-        const int c = (int)(i - e * w);
-        float val;
-        if (c < nvw) val = __ldg(v + ei[e] * nvw + c);
-        else if (c < nvw + evw) val = __ldg(e_v + e * evw + (c - nvw));
-        else val = __ldg(v + ei[E + e] * nvw + (c - nvw - evw));
-        mv[i] = val;
-    }
+template <class T>
+static int launch_gather_rows(const int64_t* ei, int64_t E, int w_node, int w_edge, const T* node, const T* edge, T* out,
+                              int sms, cudaStream_t st) {
+    const int w = 2 * w_node + w_edge;
+    CGVP_REQUIRE(w <= 1024, "gather: message row of %d columns is too wide", w);
+    const int epp = w <= 256 ? 256 / w : 1;
+    const int threads = w * epp;
+    const int64_t want = cdiv64(E, (int64_t)epp * 8);     // >= 8 edges per thread
+    const int grid = (int)(want < (int64_t)sms * 8 ? (want > 0 ? want : 1) : (int64_t)sms * 8);
+    gather_rows_kernel<T><<<grid, threads, 0, st>>>(ei, E, w_node, w_edge, node, edge, out);
+    CGVP_LAUNCH_CHECK("gather_rows_kernel");
+    return 0;
 }
 
 extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t num_edges, int32_t ns, int32_t nv,
@@ -143,18 +144,20 @@ extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t 
     if (2 * ns + es > 0) {
         CGVP_REQUIRE(ms && (ns == 0 || s) && (es == 0 || e_s), "gather: null scalar buffer");
         const bool vec = ns % 4 == 0 && es % 4 == 0 && (((uintptr_t)s | (uintptr_t)e_s | (uintptr_t)ms) & 15) == 0;
-        const int64_t total = num_edges * ((2 * ns + es) / (vec ? 4 : 1));
-        const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
-        if (vec) gather_scalar_kernel<true><<<grid, 256, 0, st>>>(edge_index, num_edges, ns, es, s, e_s, ms);
-        else gather_scalar_kernel<false><<<grid, 256, 0, st>>>(edge_index, num_edges, ns, es, s, e_s, ms);
-        CGVP_LAUNCH_CHECK("gather_scalar_kernel");
+        int rc;
+        if (vec) rc = launch_gather_rows<float4>(edge_index, num_edges, ns / 4, es / 4, reinterpret_cast<const float4*>(s),
+                                                 reinterpret_cast<const float4*>(e_s), reinterpret_cast<float4*>(ms), sms, st);
+        else rc = launch_gather_rows<float>(edge_index, num_edges, ns, es, s, e_s, ms, sms, st);
+        if (rc) return rc;
     }
     if (2 * nv + ev > 0) {
         CGVP_REQUIRE(mv && (nv == 0 || v) && (ev == 0 || e_v), "gather: null vector buffer");
-        const int64_t total = num_edges * 3 * (2 * nv + ev);
-        const int grid = (int)(cdiv64(total, 256) < (int64_t)sms * 16 ? cdiv64(total, 256) : (int64_t)sms * 16);
-        gather_vector_kernel<<<grid, 256, 0, st>>>(edge_index, num_edges, nv, ev, v, e_v, mv);
-        CGVP_LAUNCH_CHECK("gather_vector_kernel");
+        const bool vec = (3 * nv) % 4 == 0 && (3 * ev) % 4 == 0 && (((uintptr_t)v | (uintptr_t)e_v | (uintptr_t)mv) & 15) == 0;
+        int rc;
+        if (vec) rc = launch_gather_rows<float4>(edge_index, num_edges, 3 * nv / 4, 3 * ev / 4, reinterpret_cast<const float4*>(v),
+                                                 reinterpret_cast<const float4*>(e_v), reinterpret_cast<float4*>(mv), sms, st);
+        else rc = launch_gather_rows<float>(edge_index, num_edges, 3 * nv, 3 * ev, v, e_v, mv, sms, st);
+        if (rc) return rc;
     }
     cgvp_prof_end(CGVP_K_GATHER, st);
     return 0;

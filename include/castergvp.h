@@ -63,6 +63,11 @@ int32_t cgvp_sm_count(void); /* SMs of the current device (grid sizing), 0 if no
  * (csrc/conv_reg.cu, csrc/rows_reg.cu); everything else by the generic shared-memory tile kernels.  Passing 0
  * forces the generic kernels (parity tests compare the two).  Default 1. */
 int32_t cgvp_set_fast_paths(int32_t on);
+/* Precision mode of the fused GVPConv forward.  0 (default): fp32 FFMA everywhere (<= 1e-4 of the reference).
+ * 1: where a tensor-core kernel is compiled in (config-5 dims, nodes (100,16) / edges (32,1): csrc/conv_tc.cu) the
+ * W_h / W_s / W_mu / gate projections of the message GVPs run as tcgen05.mma with bf16 operands and fp32
+ * accumulation in TMEM (<= 1e-2 of the reference, the bound BASELINE.json states for tensor-core modes). */
+int32_t cgvp_set_tensor_cores(int32_t on);
 
 /* ---- kernel timing (measurement aid; no reference counterpart) ------------------------------------------------
  * When enabled, the library brackets the MAIN kernel of each operator with cudaEvents on the caller's stream.

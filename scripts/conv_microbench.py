@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--backward", action="store_true")
     ap.add_argument("--aggr", default="sum")
+    ap.add_argument("--tc", action="store_true", help="tcgen05 bf16 message GEMMs (config-5 dims)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     nd, ed = DIMS[args.dims]
@@ -46,6 +47,7 @@ def main():
         if args.backward:
             (out[0].sum() + out[1].sum()).backward()
 
+    _lib.set_tensor_cores(args.tc)
     for _ in range(3):
         run()
     torch.cuda.synchronize()

@@ -315,6 +315,39 @@ def test_fast_and_generic_kernels_agree_in_training_mode():
         assert_close(f[5][k], gnr[5][k].cpu(), TIGHT, "grad " + k, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,e,aggr,hub", [(900, 27000, "mean", False), (700, 9001, "sum", True), (200, 130, "sum", False)])
+def test_tensor_core_conv_forward_vs_oracle(n, e, aggr, hub):
+    """tcgen05 path (bf16 operands, fp32 accumulation in TMEM) of the fused GVPConv forward at config-5 dims
+    (100,16)/(32,1) against the fp64 oracle: tolerance 1e-2 (BASELINE.json: tensor-core modes), and against the fp32
+    kernels of the same library."""
+    cg = _mods()
+    from caster_dta_b200 import _lib
+    from oracle import gvp_oracle
+    import torch.nn.functional as F
+    nd, ed = (100, 16), (32, 1)
+    p, ei, x, ea = _random_layer_case(n, e, nd, ed, seed=n + e, hub=hub, aggr=aggr)
+    conv = cg.GVPConv(nd, nd, ed, aggr=aggr, activations=(F.relu, None), vector_gate=True)
+    conv.load_state_dict({k[len("conv."):]: v for k, v in p.items() if k.startswith("conv.")}, strict=True)
+    conv.to(DEV)
+    xd, ead, eid = (x[0].to(DEV), x[1].to(DEV)), (ea[0].to(DEV), ea[1].to(DEV)), ei.to(DEV)
+    with torch.no_grad():
+        ref32 = conv(xd, eid, ead)
+        _lib.set_tensor_cores(True)
+        try:
+            out = conv(xd, eid, ead)
+            out2 = conv(xd, eid, ead)
+        finally:
+            _lib.set_tensor_cores(False)
+    p64 = {k: v.double() for k, v in p.items()}
+    ref = gvp_oracle.gvp_conv(p64, "conv.", (x[0].double(), x[1].double()), ei, (ea[0].double(), ea[1].double()), aggr=aggr,
+                              scalar_act="relu", vector_act=None, vector_gate=True)
+    assert torch.equal(out[0], out2[0]) and torch.equal(out[1], out2[1]), "tensor-core path must be bit-reproducible"
+    assert_close(out[0], ref[0], 1e-2, "s (tcgen05 bf16)")
+    assert_close(out[1], ref[1], 1e-2, "V (tcgen05 bf16)")
+    assert_close(ref32[0], ref[0], TOL, "s (fp32)")
+    assert float((out[0] - ref32[0]).abs().max()) > 0, "tensor-core mode did not change the result: kernel not selected?"
+
+
 def test_conv_is_bit_reproducible_and_order_invariant():
     """Deterministic segmented aggregation: identical bits run to run; permuting the edge list changes nothing
     because the plan's stable sort restores a canonical order only up to ties -- so compare against a fresh run
