@@ -120,21 +120,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 16 consecutive fp32 columns of this thread's TMEM lane
+// 16 consecutive fp32 columns of this thread's TMEM lane.  The loads are asynchronous: issue a batch, then ONE
+// tmem_ld_wait() before the registers are read (the "+f" constraints of the wait keep the compiler from moving uses up).
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* d) {
-    uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7]), "=f"(d[8]),
+                   "=f"(d[9]), "=f"(d[10]), "=f"(d[11]), "=f"(d[12]), "=f"(d[13]), "=f"(d[14]), "=f"(d[15])
                  : "r"(addr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait(float (&d)[N]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(d[i]));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// bf16-operand mode: approximate SFU maths is far inside the mode's error budget
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 // 8 consecutive K values of one row -> one 16-byte core-matrix row
 __device__ __forceinline__ void put8(unsigned char* region, int chunk, int row, const float (&v)[8]) {
     uint4 q;
@@ -320,14 +326,16 @@ __device__ __forceinline__ void gate_and_finish(unsigned char* tile, uint32_t ws
 #pragma unroll
     for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_G + 16 * c, g + 16 * c);
 #pragma unroll
-    for (int c = 0; c < S::NV; ++c) g[c] = sigm(g[c]);
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_VO + p * S::N_V + 16 * c, v[p] + 16 * c);
+    tmem_ld_wait(g); tmem_ld_wait(v[0]); tmem_ld_wait(v[1]); tmem_ld_wait(v[2]);
+#pragma unroll
+    for (int c = 0; c < S::NV; ++c) g[c] = fast_sigmoid(g[c]);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
 #pragma unroll
         for (int c = 0; c < S::NV; ++c) v[p][c] *= g[c];                                 // :163
-    }
 }
 
 template <class S>
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                     if (k < S::ES) q8[j] = es[k < S::ES ? k : 0];
                     else if (k < S::ES + S::H0) {
                         const int o = k - S::ES < S::H0 ? (k - S::ES >= 0 ? k - S::ES : 0) : 0;
-                        q8[j] = sqrtf(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));   // :153
+                        q8[j] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));   // :153
                     } else q8[j] = k == S::ES + S::H0 ? 1.f : 0.f;
                 }
                 put8(tile + S::A_S0, c, row, q8);
@@ -446,13 +454,20 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
             mbar_wait(bar, phase);
             phase ^= 1;
             tc_fence_after();
+            {
+                constexpr int NB = S::N_S / 16, B0 = (NB + 1) / 2;      // two batches keep the temporaries small
+                float d0[16 * B0], d1[16 * (NB - B0 > 0 ? NB - B0 : 1)];
 #pragma unroll
-            for (int c = 0; c < S::N_S / 16; ++c) {
-                float d[16];
-                tmem_ld16(tm + S::C_S + 16 * c, d);
+                for (int c = 0; c < B0; ++c) tmem_ld16(tm + S::C_S + 16 * c, d0 + 16 * c);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (16 * c + j < S::NS) s[16 * c + j] += d[j];
+                for (int c = B0; c < NB; ++c) tmem_ld16(tm + S::C_S + 16 * c, d1 + 16 * (c - B0));
+                tmem_ld_wait(d0); tmem_ld_wait(d1);
+#pragma unroll
+                for (int j = 0; j < 16 * B0; ++j)
+                    if (j < S::NS) s[j < S::NS ? j : 0] += d0[j];
+#pragma unroll
+                for (int j = 16 * B0; j < 16 * NB; ++j)
+                    if (j < S::NS) s[j < S::NS ? j : 0] += d1[j - 16 * B0];
             }
             gate_and_finish<S, true>(tile, w0s + S::W_G0, tm, tm_wg, wg, row, leader, bar, phase, s, v);
         }
@@ -490,9 +505,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                 for (int q = 0; q < 3; ++q)
 #pragma unroll
                     for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_VH + q * S::N_V + 16 * c, vh[q] + 16 * c);
+                tmem_ld_wait(vh[0]); tmem_ld_wait(vh[1]); tmem_ld_wait(vh[2]);
 #pragma unroll
                 for (int o = 0; o < S::N_V; ++o)
-                    vn[o] = sqrtf(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));     // :153
+                    vn[o] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));     // :153
                 // Vh back as the A operand of W_mu (the MMAs that read V from this region have completed)
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
@@ -533,6 +549,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < S::N_S / 16; ++c) tmem_ld16(tm + S::C_S + 16 * c, s + 16 * c);
+            tmem_ld_wait(s);
             if (st == 0) gate_and_finish<S, true>(tile, wst + S::W_G, tm, tm_wg, wg, row, leader, bar, phase, s, v);
             else gate_and_finish<S, false>(tile, wst + S::W_G, tm, tm_wg, wg, row, leader, bar, phase, s, v);
         }
@@ -564,6 +581,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                 const int ra = (int)(max(ra_, p0) - p0), rb = (int)(min(rb_, p1) - p0);
                 if (ra >= rb) continue;
                 float sum = 0.f;
+#pragma unroll 4
                 for (int r = ra; r < rb; ++r) sum += M[c * 129 + r];
                 if (ra_ >= p0 && rb_ <= p1) {
                     const float f = a.mean ? 1.f / (float)max((int)(rb_ - ra_), 1) : 1.f;
