@@ -116,24 +116,55 @@ struct WarpSink {
             }
         }
         __syncwarp();
-        for (int blk = lane; blk < KA4 * NB4; blk += 32) {
-            const int a4 = blk / NB4, b4 = blk - a4 * NB4;
-            float2 c[8];
+        constexpr int NBLK = KA4 * NB4;
+        // full rounds: lane q owns block q of the round and streams all 32 rows
+#pragma unroll 1
+        for (int b0 = 0; b0 + 32 <= NBLK; b0 += 32) block_rows<KA4, NB4, NP, 32, 0>(off, b0 + lane, 0);
+        // remainder (< 32 blocks): split the 32 rows over G lane groups, then a fixed-order butterfly over the groups
+        constexpr int REM = NBLK % 32;
+        if constexpr (REM > 0) {
+            constexpr int P = REM <= 1 ? 1 : (REM <= 2 ? 2 : (REM <= 4 ? 4 : (REM <= 8 ? 8 : (REM <= 16 ? 16 : 32))));
+            constexpr int G = 32 / P;
+            const int blk = lane % P, grp = lane / P;
+            if (G == 1) { if (blk < REM) block_rows<KA4, NB4, NP, 32, 0>(off, NBLK - REM + blk, 0); }
+            else block_rows<KA4, NB4, NP, 32 / G, G>(off, NBLK - REM + (blk < REM ? blk : 0), grp * (32 / G), blk < REM && grp == 0);
+        }
+        __syncwarp();
+    }
+
+    // One 4x4 block over ROWS staged rows starting at r0.  G > 1: the partial blocks of the G lane groups are summed
+    // with G-1 shuffle exchanges (xor butterfly, fixed order) and lanes with `commit` add the result to the arena.
+    template <int KA4, int NB4, int NP, int ROWS, int G>
+    __device__ __forceinline__ void block_rows(int off, int blk, int r0, bool commit = true) {
+        constexpr int NBP = NB4 * 4;
+        const int a4 = blk / NB4, b4 = blk - a4 * NB4;
+        float2 c[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) c[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 8; ++i) c[i] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const float4* Ap = stg + (p * KA4 + a4) * CGVP_WPITCH;
-                const float4* Bp = stg + (NP * KA4 + p * NB4 + b4) * CGVP_WPITCH;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const float4 x = Ap[r], y = Bp[r];
-                    fma2(c[0], x.x, make_float2(y.x, y.y)); fma2(c[1], x.x, make_float2(y.z, y.w));
-                    fma2(c[2], x.y, make_float2(y.x, y.y)); fma2(c[3], x.y, make_float2(y.z, y.w));
-                    fma2(c[4], x.z, make_float2(y.x, y.y)); fma2(c[5], x.z, make_float2(y.z, y.w));
-                    fma2(c[6], x.w, make_float2(y.x, y.y)); fma2(c[7], x.w, make_float2(y.z, y.w));
+        for (int p = 0; p < NP; ++p) {
+            const float4* Ap = stg + (p * KA4 + a4) * CGVP_WPITCH + r0;
+            const float4* Bp = stg + (NP * KA4 + p * NB4 + b4) * CGVP_WPITCH + r0;
+#pragma unroll(ROWS < 8 ? ROWS : 8)
+            for (int r = 0; r < ROWS; ++r) {
+                const float4 x = Ap[r], y = Bp[r];
+                fma2(c[0], x.x, make_float2(y.x, y.y)); fma2(c[1], x.x, make_float2(y.z, y.w));
+                fma2(c[2], x.y, make_float2(y.x, y.y)); fma2(c[3], x.y, make_float2(y.z, y.w));
+                fma2(c[4], x.z, make_float2(y.x, y.y)); fma2(c[5], x.z, make_float2(y.z, y.w));
+                fma2(c[6], x.w, make_float2(y.x, y.y)); fma2(c[7], x.w, make_float2(y.z, y.w));
+            }
+        }
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = 32 / G; o < 32; o <<= 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    c[i].x += __shfl_xor_sync(0xffffffffu, c[i].x, o);
+                    c[i].y += __shfl_xor_sync(0xffffffffu, c[i].y, o);
                 }
             }
+        }
+        if (commit) {
             float* g = arena + off + (a4 * 4) * NBP + b4 * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -143,7 +174,6 @@ struct WarpSink {
                 *q = o;
             }
         }
-        __syncwarp();
     }
 };
 
