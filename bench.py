@@ -123,7 +123,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -351,7 +351,6 @@ def main():
         step(resident)
         b.record()
     barrier()
-    clock_info = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = launches_per_step * args.steps
     # per-kernel device time of the SAME step: the library brackets each main kernel with CUDA events on the launching
@@ -402,6 +401,7 @@ def main():
         loss_host = float(loss)                      # D2H read of the step's result (synchronises the step)
     barrier()
     e2e_sec = time.perf_counter() - t0
+    clock_info = clocks.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and e2e)
     t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -3,17 +3,22 @@
 // Replaces GVPConv.forward/message + PyG propagate (models/gvp_layers.py:291-308) like conv.cu / conv_reg.cu.
 //
 // Per CTA (one per SM, persistent): two warpgroups, each owning one 128-edge tile at a time (thread = edge = TMEM
-// lane), ping-pong on the tensor pipe.  Every W_h / W_s / W_mu(wv) / gate projection of the three message GVPs is a
-// tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM, M = 128 edges):
+// lane), ping-pong on the tensor pipe.  The projections of the three message GVPs are tcgen05.mma (kind::f16, bf16
+// operands, fp32 accumulation in TMEM, M = 128 edges):
 //     A operand  = the tile's activations, written by the owning threads as bf16 into the canonical K-major
 //                  no-swizzle layout  [k/8][row][8]  (8x16-byte core matrices, SBO = 128 B, LBO = 2048 B);
 //     B operand  = weights, pre-packed once per call into the same layout and staged into shared memory with
 //                  cp.async.bulk (TMA engine) on an mbarrier; they stay resident for the whole kernel;
 //     D          = TMEM columns, read back with tcgen05.ld.32x32b (one row per thread) for the fused epilogues:
-//                  vector norms (:153), bias rows, ReLU (:172), sigmoid gate (:158-163).
-// Linearity before the gather: the s_j / s_i blocks of W_s and the V_j / V_i blocks of W_h of the FIRST message GVP
-// act on per-node rows, so they are applied once per node (tc_node_proj_kernel) and the per-edge GEMM K drops from
-// 265 to 66; the projected rows are gathered and added in the epilogue.
+//                  vector norms (:153), ReLU (:172), sigmoid gate (:158-163).
+// Three algebraic folds keep the per-edge GEMM work and the number of MMA <-> epilogue round trips small:
+//   (1) linearity before the gather: the s_j / s_i blocks of W_s and the V_j / V_i blocks of W_h of the FIRST message
+//       GVP act on per-node rows, so they are applied once per node (tc_node_proj_kernel) and gathered; the per-edge
+//       K of that GEMM drops from 265 to 66;
+//   (2) the gate reads the PRE-activation s' (vector_act is None, :159-162), which is linear in [s ; vn ; 1]:
+//       gate = (W_sv W_s) [s ; vn ; 1] + (W_sv b_s + b_g) rides the scalar GEMM as 16 extra output columns;
+//   (3) Vo = W_mu Vh = (W_mu W_h) V rides the W_h GEMM as 16 extra output columns.
+// Per tile that leaves 1 + 2 + 2 MMA batches (was 2 + 3 + 3).  bias rows ride the GEMMs as a ones column.
 // Aggregation: deterministic segmented sum over the sorted targets (per-tile pieces + conv_fixup_kernel).
 // Accuracy: bf16 operands -> scale-relative error ~2e-3 (north star allows <= 1e-2 with tensor cores); the fp32
 // paths (conv_reg.cu / conv.cu) remain the default -- see cgvp_set_tensor_cores().
@@ -27,29 +32,33 @@ constexpr CGVP_HD inline int pad16(int x) { return (x + 15) / 16 * 16; }
 
 template <int NS_, int NV_, int ES_, int EV_>
 struct TcSpec {
-    static constexpr int NS = NS_, NV = NV_, ES = ES_, EV = EV_;
+    static constexpr int NS = NS_, NV = NV_, ES = ES_, EV = EV_, EV1 = max1(EV_);
     static constexpr int H0 = 2 * NV + EV;                       // hidden vector channels of message GVP 0
-    static constexpr int HQ = pad4(H0);                          // row pitch of the projected vector tables
-    static constexpr int SI0 = 2 * NS + ES, KSD0 = SI0 + H0;     // ws input width of GVP 0 (before the ones column)
+    static constexpr int HQ = pad4(H0);
+    static constexpr int SI0 = 2 * NS + ES, KSD0 = SI0 + H0, KSD1 = NS + NV;
     static constexpr int SOP = pad4(NS), VOP = pad4(NV), HP0 = pad4(H0), HP1 = pad4(NV);
-    // padded GEMM shapes (bf16: K multiple of 16; M = 128 needs N multiple of 16)
-    static constexpr int N_S = pad16(NS), N_V = pad16(NV);
-    static constexpr int K_S0 = pad16(ES + H0 + 1), K_V0 = pad16(H0), K_G = pad16(NS + 1), K_H = pad16(NV), K_S1 = pad16(NS + NV + 1);
-    // weight arena (bytes, bf16, [k/8][n][8] blocks)
-    static constexpr int W_S0 = 0, W_V0 = W_S0 + N_S * K_S0 * 2, W_G0 = W_V0 + N_V * K_V0 * 2, W_ST1 = W_G0 + N_V * K_G * 2;
-    static constexpr int W_H = 0, W_S = W_H + N_V * K_H * 2, W_V = W_S + N_S * K_S1 * 2, W_G = W_V + N_V * K_H * 2, W_STAGE = W_G + N_V * K_G * 2;
+    // fused scalar GEMM output row: [s' (NS -> N_S) | gate pre-activation (NV -> N_V)]
+    static constexpr int N_S = pad16(NS), N_V = pad16(NV), N_SG = N_S + N_V, N_HV = 2 * N_V;
+    static constexpr int NSG = pad4(NS + NV);                    // node-projected scalar row: [s' part | gate part]
+    static constexpr int PVW = HQ + N_V;                         // node-projected vector row per plane: [Vh | Vo]
+    static constexpr int K_S0 = pad16(ES + H0 + 1), K_H = pad16(NV), K_S1 = pad16(NS + NV + 1);
+    // bf16 weight arena (bytes, [k/8][n][8] blocks)
+    static constexpr int W_S0 = 0, W_ST1 = W_S0 + N_SG * K_S0 * 2;
+    static constexpr int W_HV = 0, W_S = W_HV + N_HV * K_H * 2, W_STAGE = W_S + N_SG * K_S1 * 2;
     static constexpr int W_BYTES = W_ST1 + 2 * W_STAGE;
-    static constexpr int WHE_FLOATS = pad4(max1(EV) * HQ);       // fp32: wh columns of the edge vector channels
+    // fp32 side arena (floats)
+    static constexpr int F_WHE = 0, F_WVOE = F_WHE + pad4(EV1 * HQ), F_WSN = F_WVOE + pad4(EV1 * N_V);
+    static constexpr int F_WVN = F_WSN + 2 * NS * NSG, F_END = F_WVN + 2 * NV * PVW;
+    static constexpr int EF = F_WSN;                             // per-edge extras kept in shared memory
     // TMEM columns per warpgroup
-    static constexpr int C_VH = 0, C_S = C_VH + 3 * N_V, C_VO = C_S + N_S, C_G = C_VO + 3 * N_V, C_END = C_G + N_V;
+    static constexpr int C_HV = 0, C_S = C_HV + 3 * N_HV, C_END = C_S + N_SG;
     static_assert(C_END <= 256, "TMEM columns per warpgroup");
     // activation tile region per warpgroup (bytes)
-    static constexpr int A_S0 = 0, A_VH0 = A_S0 + (K_S0 / 8) * 2048;
-    static constexpr int A_S1 = 0, A_V1 = A_S1 + (K_S1 / 8) * 2048;
+    static constexpr int A_S = 0, A_V = A_S + (K_S1 / 8) * 2048;
     static constexpr int CH = NS + 3 * NV, CHH = (CH + 1) / 2;   // message channels; reduced in two halves
-    static constexpr int TILE_BYTES = imax(imax(A_VH0 + 3 * (K_V0 / 8) * 2048, A_V1 + 3 * (K_H / 8) * 2048), (int)align_up(CHH * 129 * 4, 16));
-    static constexpr int WG_BYTES = TILE_BYTES + 4 * 128 * 4 + 64;   // + src/dst/eid/scale + mbarrier
-    static constexpr size_t smem_bytes() { return 1024 + (size_t)W_BYTES + WHE_FLOATS * 4 + 2 * (size_t)WG_BYTES + 64; }
+    static constexpr int TILE_BYTES = imax(imax((K_S0 / 8) * 2048, A_V + 3 * (K_H / 8) * 2048), (int)align_up(CHH * 129 * 4, 16));
+    static constexpr int WG_BYTES = TILE_BYTES + 4 * 128 * 4 + 64;   // + src/dst/eid/spare + mbarrier
+    static constexpr size_t smem_bytes() { return 1024 + (size_t)W_BYTES + EF * 4 + 2 * (size_t)WG_BYTES + 64; }
     static bool matches(const CgvpConvDesc& d) {
         using G0 = GvpC<SI0, H0, NS, NV, H0, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
         using G1 = GvpC<NS, NV, NS, NV, NV, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
@@ -64,9 +73,9 @@ struct TcArgs {
     int ntiles, mean, edge_sorted;
     const int *perm, *src, *dst, *rowptr;
     const float *e_s, *e_v;
-    const float *psj, *psi, *pvj, *pvi;     // per-node projections [N][NS], [N][NS], [N][3][HQ], [N][3][HQ]
+    const float *psj, *psi, *pvj, *pvi;     // per-node projections [N][NSG], [N][NSG], [N][3][PVW], [N][3][PVW]
     const unsigned char* wtc;               // bf16 weight arena
-    const float* whe;                       // [EV][HQ]
+    const float* wf;                        // fp32 side arena
     float *out_s, *out_v, *part_head, *part_tail;
 };
 
@@ -160,72 +169,97 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 }
 
 // ---- weight pre-packing -------------------------------------------------------------------------------------------------
-// Generic fp32 packed blocks (cgvp_common.cuh) -> bf16 [k/8][n][8] blocks of the padded GEMM shapes.
+// Generic fp32 packed blocks (cgvp_common.cuh) -> bf16 [k/8][n][8] blocks of the padded / fused GEMM shapes, plus the
+// fp32 side arena (node-projection weights and the edge-vector columns).
 template <class S>
-__global__ void tc_pack_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2,
-                               __nv_bfloat16* __restrict__ out, float* __restrict__ whe) {
+struct TcW {
     using G0 = GvpC<S::SI0, S::H0, S::NS, S::NV, S::H0, 1, 0, 1>;
     using G1 = GvpC<S::NS, S::NV, S::NS, S::NV, S::NV, 1, 0, 1>;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < S::WHE_FLOATS) {
-        const int c = i / S::HQ, o = i % S::HQ;
-        whe[i] = (c < S::EV && o < S::H0) ? w0[G0::O_WH_T + (S::NV + c) * S::HP0 + o] : 0.f;
+    // fused scalar weight of input row `row` (a row of ws_t, bias row = KSD) and fused output column n
+    template <class G>
+    static __device__ float sg(const float* w, int row, int n, bool bias_row) {
+        if (n < S::NS) return w[G::O_WS_T + row * S::SOP + n];
+        const int o = n - S::N_S;
+        if (o < 0 || o >= S::NV) return 0.f;
+        float acc = bias_row ? w[G::O_WSV_T + S::NS * S::VOP + o] : 0.f;
+        for (int j = 0; j < S::NS; ++j) acc += w[G::O_WS_T + row * S::SOP + j] * w[G::O_WSV_T + j * S::VOP + o];
+        return acc;
     }
-    if (i >= S::W_BYTES / 2) return;
+    // fused vector weight of input channel row `crow` (a row of wh_t) and output column n: [Vh (width vw) | Vo]
+    template <class G, int H, int HP>
+    static __device__ float hv(const float* w, int crow, int n, int vw) {
+        if (n < vw) return n < H ? w[G::O_WH_T + crow * HP + n] : 0.f;
+        const int o = n - vw;
+        if (o >= S::NV) return 0.f;
+        float acc = 0.f;
+        for (int h = 0; h < H; ++h) acc += w[G::O_WH_T + crow * HP + h] * w[G::O_WV_T + h * S::VOP + o];
+        return acc;
+    }
+};
+
+template <class S>
+__global__ void tc_pack_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2,
+                               __nv_bfloat16* __restrict__ out, float* __restrict__ wf) {
+    using W = TcW<S>;
+    using G0 = typename W::G0; using G1 = typename W::G1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S::F_END) {                                    // ---- fp32 side arena
+        float v = 0.f;
+        if (i < S::F_WVOE) {
+            const int c = i / S::HQ, o = i % S::HQ;
+            if (c < S::EV) v = W::template hv<G0, S::H0, S::HP0>(w0, S::NV + c, o, S::HQ);
+        } else if (i < S::F_WSN) {
+            const int j = i - S::F_WVOE, c = j / S::N_V, o = j % S::N_V;
+            if (c < S::EV) v = W::template hv<G0, S::H0, S::HP0>(w0, S::NV + c, S::HQ + o, S::HQ);
+        } else if (i < S::F_WVN) {
+            const int j = i - S::F_WSN, side = j / (S::NS * S::NSG), r = j % (S::NS * S::NSG), k = r / S::NSG, n = r % S::NSG;
+            const int row = side ? S::NS + S::ES + k : k;
+            if (n < S::NS + S::NV) v = W::template sg<G0>(w0, row, n < S::NS ? n : S::N_S + (n - S::NS), false);
+        } else {
+            const int j = i - S::F_WVN, side = j / (S::NV * S::PVW), r = j % (S::NV * S::PVW), c = r / S::PVW, n = r % S::PVW;
+            v = W::template hv<G0, S::H0, S::HP0>(w0, side ? S::NV + S::EV + c : c, n, S::HQ);
+        }
+        wf[i] = v;
+    }
+    if (i >= S::W_BYTES / 2) return;                       // ---- bf16 arena
     const int byte = 2 * i;
     float v = 0.f;
-    auto blk = [&](int off, int npad, int& n, int& k) {    // element index inside a [k/8][npad][8] block
+    int n, k;
+    auto blk = [&](int off, int npad) {                    // element (n, k) inside a [k/8][npad][8] block
         const int j = (byte - off) / 2;
         k = (j / (npad * 8)) * 8 + (j & 7);
         n = (j >> 3) % npad;
     };
-    int n, k;
-    if (byte < S::W_V0) {                                  // ws of GVP 0, edge part: [e_s ; vn ; 1]
-        blk(S::W_S0, S::N_S, n, k);
-        if (n < S::NS) {
-            if (k < S::ES) v = w0[G0::O_WS_T + (S::NS + k) * S::SOP + n];
-            else if (k < S::ES + S::H0) v = w0[G0::O_WS_T + (S::SI0 + (k - S::ES)) * S::SOP + n];
-            else if (k == S::ES + S::H0) v = w0[G0::O_WS_T + S::KSD0 * S::SOP + n];
-        }
-    } else if (byte < S::W_G0) {                           // wv of GVP 0
-        blk(S::W_V0, S::N_V, n, k);
-        if (n < S::NV && k < S::H0) v = w0[G0::O_WV_T + k * S::VOP + n];
-    } else if (byte < S::W_ST1) {                          // gate of GVP 0: [s' ; 1]
-        blk(S::W_G0, S::N_V, n, k);
-        if (n < S::NV && k <= S::NS) v = w0[G0::O_WSV_T + k * S::VOP + n];
+    if (byte < S::W_ST1) {                                 // GVP 0 scalar GEMM, edge part: [e_s ; vn ; 1]
+        blk(S::W_S0, S::N_SG);
+        if (k < S::ES) v = W::template sg<G0>(w0, S::NS + k, n, false);
+        else if (k < S::ES + S::H0) v = W::template sg<G0>(w0, S::SI0 + (k - S::ES), n, false);
+        else if (k == S::ES + S::H0) v = W::template sg<G0>(w0, S::KSD0, n, true);
     } else {
         const int st = (byte - S::W_ST1) / S::W_STAGE;
         const int base = S::W_ST1 + st * S::W_STAGE;
         const float* w = st == 0 ? w1 : w2;
-        const int b = byte - base;
-        if (b < S::W_S) {                                  // wh
-            blk(base + S::W_H, S::N_V, n, k);
-            if (n < S::NV && k < S::NV) v = w[G1::O_WH_T + k * S::HP1 + n];
-        } else if (b < S::W_V) {                           // ws: [s ; vn ; 1]
-            blk(base + S::W_S, S::N_S, n, k);
-            if (n < S::NS && k <= S::NS + S::NV) v = w[G1::O_WS_T + k * S::SOP + n];
-        } else if (b < S::W_G) {                           // wv
-            blk(base + S::W_V, S::N_V, n, k);
-            if (n < S::NV && k < S::NV) v = w[G1::O_WV_T + k * S::VOP + n];
-        } else {                                           // gate
-            blk(base + S::W_G, S::N_V, n, k);
-            if (n < S::NV && k <= S::NS) v = w[G1::O_WSV_T + k * S::VOP + n];
+        if (byte - base < S::W_S) {                        // [Vh | Vo] = [W_h ; W_mu W_h] V
+            blk(base + S::W_HV, S::N_HV);
+            if (k < S::NV) v = W::template hv<G1, S::NV, S::HP1>(w, k, n, S::N_V);
+        } else {                                           // [s' | gate] from [s ; vn ; 1]
+            blk(base + S::W_S, S::N_SG);
+            if (k <= S::KSD1) v = W::template sg<G1>(w, k, n, k == S::KSD1);
         }
     }
     out[i] = __float2bfloat16_rn(v);
 }
 
 // ---- per-node projections of message GVP 0 (fp32) -------------------------------------------------------------------------
-//   psj[n] = W_s[:, s_j block] x_s[n]      psi[n] = W_s[:, s_i block] x_s[n]
-//   pvj[n][p] = W_h[:, V_j block] x_V[n][:, p]   pvi likewise with the V_i block
+//   psj[n] = Wsn[0]^T x_s[n]   psi[n] = Wsn[1]^T x_s[n]            ([s' part | gate part], width NSG)
+//   pvj[n][p] = Wvn[0]^T x_V[n][:, p]   pvi likewise                ([Vh | Vo], width PVW)
 template <class S>
 __global__ void __launch_bounds__(256) tc_node_proj_kernel(long long N, const float* __restrict__ x_s, const float* __restrict__ x_v,
-                                                            const float* __restrict__ w0, float* __restrict__ psj,
+                                                            const float* __restrict__ wf, float* __restrict__ psj,
                                                             float* __restrict__ psi, float* __restrict__ pvj, float* __restrict__ pvi) {
-    using G0 = GvpC<S::SI0, S::H0, S::NS, S::NV, S::H0, 1, 0, 1>;
     constexpr int NB = 8;                                  // nodes per pass
-    __shared__ float xs[S::NS][NB];
-    __shared__ float xv[3 * S::NV][NB];                    // [p * NV + c][node]
+    __shared__ __align__(16) float xs[S::NS][NB];
+    __shared__ __align__(16) float xv[3 * S::NV][NB];      // [p * NV + c][node]
     const int t = threadIdx.x;
     for (long long n0 = (long long)blockIdx.x * NB; n0 < N; n0 += (long long)gridDim.x * NB) {
         __syncthreads();
@@ -239,37 +273,35 @@ __global__ void __launch_bounds__(256) tc_node_proj_kernel(long long N, const fl
         }
         __syncthreads();
         float acc[NB];
-        if (t < 2 * S::NS) {                               // scalar projections: side = t / NS, output o = t % NS
-            const int side = t / S::NS, o = t % S::NS;
-            const float* w = w0 + G0::O_WS_T + (side ? (S::NS + S::ES) : 0) * S::SOP + o;
+        for (int q = t; q < 2 * S::NSG; q += blockDim.x) {          // scalar projections: (side, output)
+            const int side = q / S::NSG, o = q % S::NSG;
+            const float* w = wf + S::F_WSN + side * S::NS * S::NSG + o;
 #pragma unroll
             for (int j = 0; j < NB; ++j) acc[j] = 0.f;
             for (int k = 0; k < S::NS; ++k) {
-                const float wk = __ldg(w + k * S::SOP);
+                const float wk = __ldg(w + k * S::NSG);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) acc[j] = fmaf(xs[k][j], wk, acc[j]);
             }
             float* out = side ? psi : psj;
 #pragma unroll
             for (int j = 0; j < NB; ++j)
-                if (n0 + j < N) out[(n0 + j) * S::NS + o] = acc[j];
+                if (n0 + j < N) out[(n0 + j) * S::NSG + o] = acc[j];
         }
-        for (int q = t; q < 2 * 3 * S::HQ; q += blockDim.x) {   // vector projections: (side, plane, o)
-            const int side = q / (3 * S::HQ), r = q % (3 * S::HQ), p = r / S::HQ, o = r % S::HQ;
+        for (int q = t; q < 2 * 3 * S::PVW; q += blockDim.x) {      // vector projections: (side, plane, output)
+            const int side = q / (3 * S::PVW), r = q % (3 * S::PVW), p = r / S::PVW, o = r % S::PVW;
+            const float* w = wf + S::F_WVN + side * S::NV * S::PVW + o;
 #pragma unroll
             for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-            if (o < S::H0) {
-                const float* w = w0 + G0::O_WH_T + (side ? (S::NV + S::EV) : 0) * S::HP0 + o;
-                for (int c = 0; c < S::NV; ++c) {
-                    const float wc = __ldg(w + c * S::HP0);
+            for (int c = 0; c < S::NV; ++c) {
+                const float wc = __ldg(w + c * S::PVW);
 #pragma unroll
-                    for (int j = 0; j < NB; ++j) acc[j] = fmaf(xv[p * S::NV + c][j], wc, acc[j]);
-                }
+                for (int j = 0; j < NB; ++j) acc[j] = fmaf(xv[p * S::NV + c][j], wc, acc[j]);
             }
             float* out = side ? pvi : pvj;
 #pragma unroll
             for (int j = 0; j < NB; ++j)
-                if (n0 + j < N) out[((n0 + j) * 3 + p) * S::HQ + o] = acc[j];
+                if (n0 + j < N) out[((n0 + j) * 3 + p) * S::PVW + o] = acc[j];
         }
     }
 }
@@ -292,50 +324,51 @@ __device__ __forceinline__ void add_row(const float* __restrict__ p, float* d) {
     }
 }
 
-// epilogue shared by the three stages: s' (pre-activation, already complete) and Vo / gate in TMEM -> (s_out, V_out)
-template <class S, bool RELU>
-__device__ __forceinline__ void gate_and_finish(unsigned char* tile, uint32_t wsm_gate, uint32_t tm, uint32_t tm_wg, int wg, int row, bool leader,
-                                                uint64_t* bar, uint32_t& phase, float (&s)[S::N_S], float (&v)[3][S::N_V]) {
-    // gate input = s' (vector_act is None), + ones column for the bias
-#pragma unroll
-    for (int c = 0; c < S::K_G / 8; ++c) {
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = 8 * c + j;
-            a[j] = k < S::NS ? s[k < S::NS ? k : 0] : (k == S::NS ? 1.f : 0.f);
-        }
-        put8(tile + S::A_S1, c, row, a);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    wg_sync(wg);
-    if (leader) {
+// One MMA batch of a warpgroup: publish the A tiles, let the leader issue, wait for completion.
+#define TC_BATCH_BEGIN()            \
+    fence_proxy_async();            \
+    tc_fence_before();              \
+    wg_sync(wg);                    \
+    if (leader) {                   \
         tc_fence_after();
-        issue_gemm<S::N_V, S::K_G>(tm_wg + S::C_G, smem_u32(tile + S::A_S1), wsm_gate);
-        mma_commit(bar);
+#define TC_BATCH_COMMIT()           \
+        mma_commit(bar);            \
+    }
+#define TC_BATCH_WAIT()             \
+    mbar_wait(bar, phase);          \
+    phase ^= 1;                     \
+    tc_fence_after();
+
+// [s' | gate] in TMEM (+ optional addend already in sg) and vo in registers -> (s_out, V_out)
+template <class S, bool RELU, bool ADD>
+__device__ __forceinline__ void finish_stage(uint32_t tm, float (&sg)[S::N_SG], float (&vo)[3][S::N_V]) {
+    if (ADD) {
+        constexpr int NB = S::N_SG / 16, B0 = (NB + 1) / 2;
+        float d0[16 * B0], d1[16 * (NB - B0 > 0 ? NB - B0 : 1)];
+#pragma unroll
+        for (int c = 0; c < B0; ++c) tmem_ld16(tm + S::C_S + 16 * c, d0 + 16 * c);
+#pragma unroll
+        for (int c = B0; c < NB; ++c) tmem_ld16(tm + S::C_S + 16 * c, d1 + 16 * (c - B0));
+        tmem_ld_wait(d0); tmem_ld_wait(d1);
+#pragma unroll
+        for (int j = 0; j < 16 * B0; ++j) sg[j] += d0[j];
+#pragma unroll
+        for (int j = 16 * B0; j < 16 * NB; ++j) sg[j] += d1[j - 16 * B0];
+    } else {
+#pragma unroll
+        for (int c = 0; c < S::N_SG / 16; ++c) tmem_ld16(tm + S::C_S + 16 * c, sg + 16 * c);
+        tmem_ld_wait(sg);
+    }
+#pragma unroll
+    for (int c = 0; c < S::NV; ++c) {
+        const float g = fast_sigmoid(sg[S::N_S + c]);                                   // :158-163
+#pragma unroll
+        for (int p = 0; p < 3; ++p) vo[p][c] *= g;
     }
     if (RELU) {
 #pragma unroll
-        for (int k = 0; k < S::NS; ++k) s[k] = fmaxf(s[k], 0.f);                        // :172-173 (after the gate input was taken)
+        for (int k = 0; k < S::NS; ++k) sg[k] = fmaxf(sg[k], 0.f);                       // :172-173
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    float g[S::N_V];
-#pragma unroll
-    for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_G + 16 * c, g + 16 * c);
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_VO + p * S::N_V + 16 * c, v[p] + 16 * c);
-    tmem_ld_wait(g); tmem_ld_wait(v[0]); tmem_ld_wait(v[1]); tmem_ld_wait(v[2]);
-#pragma unroll
-    for (int c = 0; c < S::NV; ++c) g[c] = fast_sigmoid(g[c]);
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int c = 0; c < S::NV; ++c) v[p][c] *= g[c];                                 // :163
 }
 
 template <class S>
@@ -343,14 +376,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* wsm = smem;
-    float* whe = reinterpret_cast<float*>(smem + S::W_BYTES);
-    unsigned char* wgbase = smem + S::W_BYTES + S::WHE_FLOATS * 4;
+    float* ef = reinterpret_cast<float*>(smem + S::W_BYTES);           // whe | wvoe
+    unsigned char* wgbase = smem + S::W_BYTES + S::EF * 4;
     const int tid = threadIdx.x, wg = tid >> 7, row = tid & 127, warp = tid >> 5;
     unsigned char* tile = wgbase + wg * S::WG_BYTES;
     int* isrc = reinterpret_cast<int*>(tile + S::TILE_BYTES);
     int* idst = isrc + 128;
     int* ieid = idst + 128;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(ieid + 2 * 128);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tile + S::TILE_BYTES + 4 * 128 * 4);
     uint64_t* wbar = reinterpret_cast<uint64_t*>(wgbase + 2 * S::WG_BYTES);
     uint32_t* slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
@@ -361,7 +394,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(slot, 512);
-    for (int i = tid; i < S::WHE_FLOATS; i += blockDim.x) whe[i] = a.whe[i];
+    for (int i = tid; i < S::EF; i += blockDim.x) ef[i] = a.wf[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -371,12 +404,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
         for (int off = 0; off < S::W_BYTES; off += CHUNK)
             bulk_g2s(wsm + off, a.wtc + off, (uint32_t)(S::W_BYTES - off < CHUNK ? S::W_BYTES - off : CHUNK), wbar);
     }
-    const uint32_t tm = *slot + (uint32_t)(wg * 256) + ((uint32_t)((warp & 3) * 32) << 16);   // this thread's lane, this WG's columns
-    const uint32_t tm_wg = *slot + (uint32_t)(wg * 256);                                       // MMA destination (lane 0)
+    const uint32_t tm_wg = *slot + (uint32_t)(wg * 256);                          // MMA destination (lane 0)
+    const uint32_t tm = tm_wg + ((uint32_t)((warp & 3) * 32) << 16);               // this thread's lane
     mbar_wait(wbar, 0);
     uint32_t phase = 0;
     const bool leader = row == 0;
     const uint32_t w0s = smem_u32(wsm);
+    const float* whe = ef + S::F_WHE;
+    const float* wvoe = ef + S::F_WVOE;
 
     for (int t = blockIdx.x * 2 + wg; t < a.ntiles; t += gridDim.x * 2) {
         const long long p0 = (long long)t * 128;
@@ -387,31 +422,36 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
         wg_sync(wg);                                        // previous tile's reduce is done with the tile region / index arrays
         isrc[row] = src; idst[row] = dst; ieid[row] = (int)eid;
 
-        float s[S::N_S], v[3][S::N_V];
-#pragma unroll
-        for (int k = S::NS; k < S::N_S; ++k) s[k] = 0.f;
+        float sg[S::N_SG], v[3][S::N_V];
         // ================= message GVP 0 =================
         {
-            // Vh = W_h [V_j ; e_V ; V_i] = pvj[src] + pvi[dst] + sum_c e_V[c] (x) whe[c]                       :152
+            // [Vh | Vo] = node projections + edge-vector columns                                                   :152,:156
             float vh[3][S::HQ];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                ld_row<S::HQ>(a.pvj + ((long long)src * 3 + q) * S::HQ, vh[q]);
-                add_row<S::HQ>(a.pvi + ((long long)dst * 3 + q) * S::HQ, vh[q]);
+                const float* pj = a.pvj + ((long long)src * 3 + q) * S::PVW;
+                const float* pi = a.pvi + ((long long)dst * 3 + q) * S::PVW;
+                ld_row<S::HQ>(pj, vh[q]);
+                add_row<S::HQ>(pi, vh[q]);
+                ld_row<S::N_V>(pj + S::HQ, v[q]);
+                add_row<S::N_V>(pi + S::HQ, v[q]);
             }
             if constexpr (S::EV > 0) {
 #pragma unroll
                 for (int c = 0; c < S::EV; ++c) {
-                    const float ex = __ldg(a.e_v + (eid * S::EV + c) * 3), ey = __ldg(a.e_v + (eid * S::EV + c) * 3 + 1),
-                                ez = __ldg(a.e_v + (eid * S::EV + c) * 3 + 2);
+                    float e3[3];
 #pragma unroll
-                    for (int o = 0; o < S::H0; ++o) {
-                        const float w = whe[c * S::HQ + o];
-                        vh[0][o] = fmaf(ex, w, vh[0][o]); vh[1][o] = fmaf(ey, w, vh[1][o]); vh[2][o] = fmaf(ez, w, vh[2][o]);
+                    for (int q = 0; q < 3; ++q) e3[q] = __ldg(a.e_v + (eid * S::EV + c) * 3 + q);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                        for (int o = 0; o < S::H0; ++o) vh[q][o] = fmaf(e3[q], whe[c * S::HQ + o], vh[q][o]);
+#pragma unroll
+                        for (int o = 0; o < S::NV; ++o) v[q][o] = fmaf(e3[q], wvoe[c * S::N_V + o], v[q][o]);
                     }
                 }
             }
-            // A operands: [e_s ; vn ; 1] for W_s (edge part) and Vh (3 planes) for W_mu
+            // A operand [e_s ; vn ; 1]
             float es[S::ES];
             ld_row<S::ES>(a.e_s + eid * S::ES, es);
 #pragma unroll
@@ -422,60 +462,33 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                     const int k = 8 * c + j;
                     if (k < S::ES) q8[j] = es[k < S::ES ? k : 0];
                     else if (k < S::ES + S::H0) {
-                        const int o = k - S::ES < S::H0 ? (k - S::ES >= 0 ? k - S::ES : 0) : 0;
+                        const int o = (k - S::ES >= 0 && k - S::ES < S::H0) ? k - S::ES : 0;
                         q8[j] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));   // :153
                     } else q8[j] = k == S::ES + S::H0 ? 1.f : 0.f;
                 }
-                put8(tile + S::A_S0, c, row, q8);
+                put8(tile + S::A_S, c, row, q8);
             }
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int c = 0; c < S::K_V0 / 8; ++c) {
-                    float q8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const int o = 8 * c + j; q8[j] = o < S::H0 ? vh[q][o < S::H0 ? o : 0] : 0.f; }
-                    put8(tile + S::A_VH0 + q * (S::K_V0 / 8) * 2048, c, row, q8);
-                }
-            fence_proxy_async();
-            tc_fence_before();
-            wg_sync(wg);
-            if (leader) {
-                tc_fence_after();
-                issue_gemm<S::N_S, S::K_S0>(tm_wg + S::C_S, smem_u32(tile + S::A_S0), w0s + S::W_S0);
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    issue_gemm<S::N_V, S::K_V0>(tm_wg + S::C_VO + q * S::N_V, smem_u32(tile + S::A_VH0 + q * (S::K_V0 / 8) * 2048), w0s + S::W_V0);
-                mma_commit(bar);
-            }
-            // while the tensor pipe works: the node-projected part of s'
-            ld_row<S::NS>(a.psj + (long long)src * S::NS, s);
-            add_row<S::NS>(a.psi + (long long)dst * S::NS, s);
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
+            TC_BATCH_BEGIN()
+                issue_gemm<S::N_SG, S::K_S0>(tm_wg + S::C_S, smem_u32(tile + S::A_S), w0s + S::W_S0);
+            TC_BATCH_COMMIT()
+            // while the tensor pipe works: the node-projected part of [s' | gate]
             {
-                constexpr int NB = S::N_S / 16, B0 = (NB + 1) / 2;      // two batches keep the temporaries small
-                float d0[16 * B0], d1[16 * (NB - B0 > 0 ? NB - B0 : 1)];
+                float* g = sg;
+                ld_row<S::NS>(a.psj + (long long)src * S::NSG, g);
+                add_row<S::NS>(a.psi + (long long)dst * S::NSG, g);
 #pragma unroll
-                for (int c = 0; c < B0; ++c) tmem_ld16(tm + S::C_S + 16 * c, d0 + 16 * c);
-#pragma unroll
-                for (int c = B0; c < NB; ++c) tmem_ld16(tm + S::C_S + 16 * c, d1 + 16 * (c - B0));
-                tmem_ld_wait(d0); tmem_ld_wait(d1);
-#pragma unroll
-                for (int j = 0; j < 16 * B0; ++j)
-                    if (j < S::NS) s[j < S::NS ? j : 0] += d0[j];
-#pragma unroll
-                for (int j = 16 * B0; j < 16 * NB; ++j)
-                    if (j < S::NS) s[j < S::NS ? j : 0] += d1[j - 16 * B0];
+                for (int k = S::NS; k < S::N_S; ++k) sg[k] = 0.f;
+                ld_row<S::N_V>(a.psj + (long long)src * S::NSG + S::NS, g + S::N_S);
+                add_row<S::N_V>(a.psi + (long long)dst * S::NSG + S::NS, g + S::N_S);
             }
-            gate_and_finish<S, true>(tile, w0s + S::W_G0, tm, tm_wg, wg, row, leader, bar, phase, s, v);
+            TC_BATCH_WAIT()
+            finish_stage<S, true, true>(tm, sg, v);
         }
         // ================= message GVPs 1 and 2 =================
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
             const uint32_t wst = w0s + S::W_ST1 + st * S::W_STAGE;
-            // Vh = W_h V                                                                                          :152
+            // [Vh | Vo] = [W_h ; W_mu W_h] V                                                                       :152,:156
 #pragma unroll
             for (int q = 0; q < 3; ++q)
 #pragma unroll
@@ -483,75 +496,58 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                     float q8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { const int o = 8 * c + j; q8[j] = o < S::NV ? v[q][o < S::NV ? o : 0] : 0.f; }
-                    put8(tile + S::A_V1 + q * (S::K_H / 8) * 2048, c, row, q8);
+                    put8(tile + S::A_V + q * (S::K_H / 8) * 2048, c, row, q8);
                 }
-            fence_proxy_async();
-            tc_fence_before();
-            wg_sync(wg);
-            if (leader) {
-                tc_fence_after();
+            TC_BATCH_BEGIN()
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
-                    issue_gemm<S::N_V, S::K_H>(tm_wg + S::C_VH + q * S::N_V, smem_u32(tile + S::A_V1 + q * (S::K_H / 8) * 2048), wst + S::W_H);
-                mma_commit(bar);
+                    issue_gemm<S::N_HV, S::K_H>(tm_wg + S::C_HV + q * S::N_HV, smem_u32(tile + S::A_V + q * (S::K_H / 8) * 2048), wst + S::W_HV);
+            TC_BATCH_COMMIT()
+            // meanwhile: the scalar part of the next A operand
+#pragma unroll
+            for (int c = 0; c < S::NS / 8; ++c) {
+                float q8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q8[j] = sg[8 * c + j];
+                put8(tile + S::A_S, c, row, q8);
             }
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
+            TC_BATCH_WAIT()
             float vn[S::N_V];
             {
                 float vh[3][S::N_V];
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
+                for (int q = 0; q < 3; ++q) {
 #pragma unroll
-                    for (int c = 0; c < S::N_V / 16; ++c) tmem_ld16(tm + S::C_VH + q * S::N_V + 16 * c, vh[q] + 16 * c);
+                    for (int c = 0; c < S::N_V / 16; ++c) {
+                        tmem_ld16(tm + S::C_HV + q * S::N_HV + 16 * c, vh[q] + 16 * c);
+                        tmem_ld16(tm + S::C_HV + q * S::N_HV + S::N_V + 16 * c, v[q] + 16 * c);
+                    }
+                }
                 tmem_ld_wait(vh[0]); tmem_ld_wait(vh[1]); tmem_ld_wait(vh[2]);
+                tmem_ld_wait(v[0]); tmem_ld_wait(v[1]); tmem_ld_wait(v[2]);
 #pragma unroll
                 for (int o = 0; o < S::N_V; ++o)
                     vn[o] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));     // :153
-                // Vh back as the A operand of W_mu (the MMAs that read V from this region have completed)
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int c = 0; c < S::K_H / 8; ++c) {
-                        float q8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const int o = 8 * c + j; q8[j] = o < S::NV ? vh[q][o < S::NV ? o : 0] : 0.f; }
-                        put8(tile + S::A_V1 + q * (S::K_H / 8) * 2048, c, row, q8);
-                    }
             }
-            // [s ; vn ; 1]
+            // rest of [s ; vn ; 1]
 #pragma unroll
-            for (int c = 0; c < S::K_S1 / 8; ++c) {
+            for (int c = S::NS / 8; c < S::K_S1 / 8; ++c) {
                 float q8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int k = 8 * c + j;
-                    if (k < S::NS) q8[j] = s[k < S::NS ? k : 0];
-                    else if (k < S::NS + S::NV) q8[j] = vn[k - S::NS < S::NV ? (k - S::NS >= 0 ? k - S::NS : 0) : 0];
+                    if (k < S::NS) q8[j] = sg[k < S::NS ? k : 0];
+                    else if (k < S::NS + S::NV) q8[j] = vn[(k - S::NS >= 0 && k - S::NS < S::NV) ? k - S::NS : 0];
                     else q8[j] = k == S::NS + S::NV ? 1.f : 0.f;
                 }
-                put8(tile + S::A_S1, c, row, q8);
+                put8(tile + S::A_S, c, row, q8);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            wg_sync(wg);
-            if (leader) {
-                tc_fence_after();
-                issue_gemm<S::N_S, S::K_S1>(tm_wg + S::C_S, smem_u32(tile + S::A_S1), wst + S::W_S);
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    issue_gemm<S::N_V, S::K_H>(tm_wg + S::C_VO + q * S::N_V, smem_u32(tile + S::A_V1 + q * (S::K_H / 8) * 2048), wst + S::W_V);
-                mma_commit(bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < S::N_S / 16; ++c) tmem_ld16(tm + S::C_S + 16 * c, s + 16 * c);
-            tmem_ld_wait(s);
-            if (st == 0) gate_and_finish<S, true>(tile, wst + S::W_G, tm, tm_wg, wg, row, leader, bar, phase, s, v);
-            else gate_and_finish<S, false>(tile, wst + S::W_G, tm, tm_wg, wg, row, leader, bar, phase, s, v);
+            TC_BATCH_BEGIN()
+                issue_gemm<S::N_SG, S::K_S1>(tm_wg + S::C_S, smem_u32(tile + S::A_S), wst + S::W_S);
+            TC_BATCH_COMMIT()
+            TC_BATCH_WAIT()
+            if (st == 0) finish_stage<S, true, false>(tm, sg, v);
+            else finish_stage<S, false, false>(tm, sg, v);
         }
         // ================= aggregation: segmented sum over the sorted targets, two channel halves =================
         tc_fence_before();
@@ -567,7 +563,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_consta
                 const int ch = ch0 + c;
                 if (ch < S::CH) {
                     float val;
-                    if (ch < S::NS) val = s[ch < S::NS ? ch : 0];
+                    if (ch < S::NS) val = sg[ch < S::NS ? ch : 0];
                     else { const int j = ch - S::NS >= 0 ? ch - S::NS : 0; val = v[j % 3][(j / 3) < S::NV ? j / 3 : 0]; }
                     M[c * 129 + row] = val;
                 }
@@ -615,8 +611,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int64_t conv_tc_workspace_bytes(const CgvpConvDesc* desc, int64_t E, int64_t N) {
     using S = TcMb;
     if (!S::matches(*desc)) return 0;
-    int64_t b = align_up(S::W_BYTES, 256) + align_up(S::WHE_FLOATS * 4, 256);
-    b += 2 * align_up(N * S::NS * 4, 256) + 2 * align_up(N * 3 * S::HQ * 4, 256);
+    int64_t b = align_up(S::W_BYTES, 256) + align_up(S::F_END * 4, 256);
+    b += 2 * align_up(N * S::NSG * 4, 256) + 2 * align_up(N * 3 * S::PVW * 4, 256);
     b += 2 * align_up(cdiv64(E > 0 ? E : 1, 128) * S::CH * 4, 256);
     return b + 256;
 }
@@ -633,24 +629,24 @@ int conv_fwd_tc(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s
     char* b = reinterpret_cast<char*>(tcws);
     b = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(b) + 255) & ~(uintptr_t)255);
     unsigned char* wtc = reinterpret_cast<unsigned char*>(b); b += align_up(S::W_BYTES, 256);
-    float* whe = reinterpret_cast<float*>(b); b += align_up(S::WHE_FLOATS * 4, 256);
-    float* psj = reinterpret_cast<float*>(b); b += align_up(N * S::NS * 4, 256);
-    float* psi = reinterpret_cast<float*>(b); b += align_up(N * S::NS * 4, 256);
-    float* pvj = reinterpret_cast<float*>(b); b += align_up(N * 3 * S::HQ * 4, 256);
-    float* pvi = reinterpret_cast<float*>(b); b += align_up(N * 3 * S::HQ * 4, 256);
+    float* wf = reinterpret_cast<float*>(b); b += align_up(S::F_END * 4, 256);
+    float* psj = reinterpret_cast<float*>(b); b += align_up(N * S::NSG * 4, 256);
+    float* psi = reinterpret_cast<float*>(b); b += align_up(N * S::NSG * 4, 256);
+    float* pvj = reinterpret_cast<float*>(b); b += align_up(N * 3 * S::PVW * 4, 256);
+    float* pvi = reinterpret_cast<float*>(b); b += align_up(N * 3 * S::PVW * 4, 256);
     const int64_t ntiles = cdiv64(E, 128);
     float* part_head = reinterpret_cast<float*>(b); b += align_up(ntiles * S::CH * 4, 256);
     float* part_tail = reinterpret_cast<float*>(b);
     const int sms = cgvp_num_sms();
     auto fail = [&](cudaError_t e, const char* what) { cgvp_set_error("%s failed: %s", what, cudaGetErrorString(e)); *rc_out = (int)e; return 1; };
-    tc_pack_kernel<S><<<cdiv(S::W_BYTES / 2, 256), 256, 0, st>>>(h_packed[0], h_packed[1], h_packed[2],
-                                                                 reinterpret_cast<__nv_bfloat16*>(wtc), whe);
-    tc_node_proj_kernel<S><<<(int)min((long long)cdiv64(N, 8), (long long)sms * 8), 256, 0, st>>>(N, x_s, x_v, h_packed[0], psj, psi, pvj, pvi);
+    const int pack_threads = S::W_BYTES / 2 > S::F_END ? S::W_BYTES / 2 : S::F_END;
+    tc_pack_kernel<S><<<cdiv(pack_threads, 128), 128, 0, st>>>(h_packed[0], h_packed[1], h_packed[2], reinterpret_cast<__nv_bfloat16*>(wtc), wf);
+    tc_node_proj_kernel<S><<<(int)min((long long)cdiv64(N, 8), (long long)sms * 8), 256, 0, st>>>(N, x_s, x_v, wf, psj, psi, pvj, pvi);
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.E = E; a.N = N; a.ntiles = (int)ntiles; a.mean = desc->aggr == CGVP_AGGR_MEAN; a.edge_sorted = desc->edge_sorted;
     a.perm = plan->perm; a.src = plan->src; a.dst = plan->dst; a.rowptr = plan->rowptr;
-    a.e_s = e_s; a.e_v = e_v; a.psj = psj; a.psi = psi; a.pvj = pvj; a.pvi = pvi; a.wtc = wtc; a.whe = whe;
+    a.e_s = e_s; a.e_v = e_v; a.psj = psj; a.psi = psi; a.pvj = pvj; a.pvi = pvi; a.wtc = wtc; a.wf = wf;
     a.out_s = out_s; a.out_v = out_v; a.part_head = part_head; a.part_tail = part_tail;
     const size_t smem = S::smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
