@@ -10,6 +10,8 @@ int rows_fwd_special(const CgvpRowDesc* desc, const CgvpRowArgs* args, cudaStrea
 int rows_bwd_special(const CgvpRowDesc* desc, const CgvpRowArgs* args, const CgvpRowGradArgs* grads, void* ws, int64_t ws_bytes,
                      cudaStream_t st, int* rc);
 int rows_special_partial_floats(const CgvpRowDesc* desc);
+int64_t rows_wide_workspace_bytes(const CgvpRowDesc* desc, int64_t rows);
+int rows_fwd_wide(const CgvpRowDesc* desc, const CgvpRowArgs* args, void* ws, int64_t ws_bytes, cudaStream_t st, int* rc);
 
 struct RowsK {
     int in_s, in_v, onehot, has_res, pre_norm, n_gvp, post_res, post_norm;
@@ -411,7 +413,7 @@ static int choose_geometry(RowsK& K, int smem_max, size_t* smem_bytes) {
 }
 
 extern "C" int64_t cgvp_rows_workspace_bytes(const CgvpRowDesc* desc, int64_t rows, int32_t backward) {
-    if (!backward) return 16;
+    if (!backward) return 16 + rows_wide_workspace_bytes(desc, rows);
     RowsK K;
     if (build_rows_k(desc, true, K)) return -1;
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
@@ -441,6 +443,7 @@ extern "C" int32_t cgvp_rows_fwd(const CgvpRowDesc* desc, const CgvpRowArgs* arg
     if (args->rows == 0) return 0;
     {   // register-resident specialised kernels for the dims they were compiled for (rows_reg.cu)
         int rc = 0;
+        if (rows_fwd_wide(desc, args, ws, ws_bytes, (cudaStream_t)stream, &rc)) return rc;
         if (rows_fwd_special(desc, args, (cudaStream_t)stream, &rc)) return rc;
     }
     size_t smem = 0;

@@ -212,7 +212,10 @@ class RowsFunction(torch.autograd.Function):
         t["out_s"] = torch.empty(rows, prog.out_s, dtype=torch.float32, device=dev)
         t["out_v"] = torch.empty(rows, prog.out_v, 3, dtype=torch.float32, device=dev)
         a, blocks = _row_args(prog, rows, t, arena, offs)
-        _lib.timed_call("cgvp_rows_fwd", lib().cgvp_rows_fwd, C.byref(prog.desc), C.byref(a), None, 0, _stream())
+        nbytes = lib().cgvp_rows_workspace_bytes(C.byref(prog.desc), rows, 0)
+        ws = _workspace(nbytes, dev)
+        wp, wn = _aligned_ptr(ws)
+        _lib.timed_call("cgvp_rows_fwd", lib().cgvp_rows_fwd, C.byref(prog.desc), C.byref(a), wp, wn, _stream())
         out_s, out_v = t.pop("out_s"), t.pop("out_v")     # never keep the outputs on ctx: node -> output -> node leaks
         ctx.prog, ctx.t, ctx.arena, ctx.offs, ctx.rows = prog, t, arena, offs, rows
         ctx.weights = weights
