@@ -110,11 +110,71 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restr
     const int kind = c < w_node ? 0 : (c < w_node + w_edge ? 1 : 2);
     const int off = kind == 0 ? c : (kind == 1 ? c - w_node : c - w_node - w_edge);
     const int64_t stride = (int64_t)gridDim.x * epp;
-    for (int64_t e = (int64_t)blockIdx.x * epp + de; e < E; e += stride) {
+    constexpr int U = 2;                            // edges in flight per thread: index loads, then row loads, then stores
+    int64_t e = (int64_t)blockIdx.x * epp + de;
+    for (; e + (U - 1) * stride < E; e += U * stride) {
+        const T* p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t eu = e + u * stride;
+            p[u] = kind == 1 ? edge + eu * w_edge + off : node + __ldg(ei + (kind == 0 ? eu : E + eu)) * w_node + off;
+        }
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = kind == 1 ? __ldcs(p[u]) : __ldg(p[u]);     // edge rows stream, node rows are reused
+#pragma unroll
+        for (int u = 0; u < U; ++u) __stcs(out + (e + u * stride) * w + c, v[u]);       // the output is never re-read here
+    }
+    for (; e < E; e += stride) {
         T v;
         if (kind == 1) v = __ldg(edge + e * w_edge + off);
         else v = __ldg(node + __ldg(ei + (kind == 0 ? e : E + e)) * w_node + off);
         out[e * w + c] = v;
+    }
+}
+
+// Rows whose width is not a multiple of 16 bytes (the vector part: 3 * (2 nv + ev) floats): a CTA assembles
+// GV_EDGES message rows in shared memory (float4 loads of the node rows where they are 16-byte aligned, scalars for
+// the rest) and writes the assembled chunk -- contiguous in the output -- with coalesced float4 stores.
+#define GV_EDGES 64
+__global__ void __launch_bounds__(256) gather_staged_kernel(const int64_t* __restrict__ ei, int64_t E, int w_node, int w_edge,
+                                                            const float* __restrict__ node, const float* __restrict__ edge,
+                                                            float* __restrict__ out, int node_vec4) {
+    extern __shared__ __align__(16) float gbuf[];
+    const int w = 2 * w_node + w_edge;
+    const int nq = node_vec4 ? w_node / 4 : w_node;        // load units per node row
+    const int units = 2 * nq + w_edge;                     // per edge
+    const int64_t nchunks = cdiv64(E, GV_EDGES);
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t e0 = ch * GV_EDGES;
+        const int ne = (int)(E - e0 < GV_EDGES ? E - e0 : GV_EDGES);
+        for (int i = threadIdx.x; i < ne * units; i += blockDim.x) {
+            const int le = i / units, u = i - le * units;
+            const int64_t e = e0 + le;
+            float* dst = gbuf + le * w;
+            if (u < 2 * nq) {
+                const int side = u >= nq, j = side ? u - nq : u;
+                const int64_t n = __ldg(ei + (side ? E + e : e));
+                float* d = dst + (side ? w_node + w_edge : 0);
+                if (node_vec4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(node + n * w_node) + j);
+                    d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+                } else {
+                    d[j] = __ldg(node + n * w_node + j);
+                }
+            } else {
+                const int j = u - 2 * nq;
+                dst[w_node + j] = __ldg(edge + e * w_edge + j);
+            }
+        }
+        __syncthreads();
+        const int total = ne * w;                          // floats of this chunk; its start e0 * w * 4 bytes is 16-byte aligned
+        float* o = out + e0 * w;
+        const int t4 = total >> 2;
+        for (int i = threadIdx.x; i < t4; i += blockDim.x)
+            __stcs(reinterpret_cast<float4*>(o) + i, reinterpret_cast<const float4*>(gbuf)[i]);
+        for (int i = (t4 << 2) + threadIdx.x; i < total; i += blockDim.x) o[i] = gbuf[i];
+        __syncthreads();
     }
 }
 
@@ -156,7 +216,15 @@ extern "C" int32_t cgvp_gather_message_input(const int64_t* edge_index, int64_t 
         int rc;
         if (vec) rc = launch_gather_rows<float4>(edge_index, num_edges, 3 * nv / 4, 3 * ev / 4, reinterpret_cast<const float4*>(v),
                                                  reinterpret_cast<const float4*>(e_v), reinterpret_cast<float4*>(mv), sms, st);
-        else rc = launch_gather_rows<float>(edge_index, num_edges, 3 * nv, 3 * ev, v, e_v, mv, sms, st);
+        else if ((((uintptr_t)mv) & 15) == 0 && (size_t)GV_EDGES * 3 * (2 * nv + ev) * 4 <= 48 * 1024) {
+            const int node_vec4 = (3 * nv) % 4 == 0 && (((uintptr_t)v) & 15) == 0;
+            const int64_t nch = cdiv64(num_edges, GV_EDGES);
+            const int grid = (int)(nch < (int64_t)sms * 8 ? nch : (int64_t)sms * 8);
+            gather_staged_kernel<<<grid, 256, (size_t)GV_EDGES * 3 * (2 * nv + ev) * 4, st>>>(edge_index, num_edges, 3 * nv, 3 * ev, v, e_v,
+                                                                                           mv, node_vec4);
+            CGVP_LAUNCH_CHECK("gather_staged_kernel");
+            rc = 0;
+        } else rc = launch_gather_rows<float>(edge_index, num_edges, 3 * nv, 3 * ev, v, e_v, mv, sms, st);
         if (rc) return rc;
     }
     cgvp_prof_end(CGVP_K_GATHER, st);

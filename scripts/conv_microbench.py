@@ -52,9 +52,13 @@ def main():
         run()
     torch.cuda.synchronize()
     _lib.profile_enable(True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
     for _ in range(args.iters):
         run()
+    t1.record()
     torch.cuda.synchronize()
+    layer_ms = t0.elapsed_time(t1) / args.iters
     prof = _lib.profile_collect()
     peak = 6555.8
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -62,7 +66,12 @@ def main():
         peak = json.load(open(pk))["hbm_gbs"]
     r, q, i, kbar = 4 * nd[0] + 12 * nd[1], 4 * ed[0] + 12 * ed[1], 16, e / n
     alg = {"conv_fwd": q + i + 2 * r / kbar, "conv_bwd": 2 * q + i + 3 * r / kbar}
-    res = {"dims": args.dims, "nodes": n, "edges": e, "kernels": {}}
+    flops_edge = {"ck": 5342, "mb": 132820}[args.dims]     # GVPConvLayer forward FLOP per edge at kbar = 30
+    res = {"dims": args.dims, "nodes": n, "edges": e, "tensor_cores": bool(args.tc), "backward": bool(args.backward),
+           "layer": {"ms": layer_ms, "edges_per_s": e / (layer_ms * 1e-3),
+                     "reference_TFLOPs": flops_edge * (3 if args.backward else 1) * e / (layer_ms * 1e-3) / 1e12,
+                     "note": "whole GVPConvLayer call incl. weight packing and Python launch overhead, CUDA events"},
+           "kernels": {}}
     for name, (ms, cnt) in prof.items():
         if not cnt:
             continue
