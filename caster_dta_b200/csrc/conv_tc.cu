@@ -2,26 +2,23 @@
 // nodes (100,16), edges (32,1), message chain GVP(relu,gate) -> GVP(relu,gate) -> GVP(none,gate).
 // Replaces GVPConv.forward/message + PyG propagate (models/gvp_layers.py:291-308) like conv.cu / conv_reg.cu.
 //
-// Per CTA (one per SM, persistent, 512 threads): two groups of 256 threads, each owning one 128-edge tile at a time and
-// ping-ponging on the tensor pipe.  Inside a group, edge row r (= TMEM lane r) is shared by TWO threads, each owning half
-// of the row's columns (so 16 warps fit in the register file and the per-thread epilogue halves).  The projections
-// of the three message GVPs are tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in TMEM, M = 128 edges):
+// Per CTA (one per SM, persistent): two warpgroups, each owning one 128-edge tile at a time (thread = edge = TMEM
+// lane), ping-pong on the tensor pipe.  The projections of the three message GVPs are tcgen05.mma (kind::f16, bf16
+// operands, fp32 accumulation in TMEM, M = 128 edges):
 //     A operand  = the tile's activations, written by the owning threads as bf16 into the canonical K-major
 //                  no-swizzle layout  [k/8][row][8]  (8x16-byte core matrices, SBO = 128 B, LBO = 2048 B);
 //     B operand  = weights, pre-packed once per call into the same layout and staged into shared memory with
 //                  cp.async.bulk (TMA engine) on an mbarrier; they stay resident for the whole kernel;
-//     D          = TMEM columns, read back with tcgen05.ld.32x32b for the fused epilogues: vector norms (:153),
-//                  ReLU (:172), sigmoid gate (:158-163).
-// The K / N orders of every GEMM are chosen so that each half-row thread reads and writes only contiguous chunks:
-// output row of the scalar GEMM = [s'_h0 | gate_h0 | s'_h1 | gate_h1], its input row = [s_h0 | vn_h0 | s_h1 (+ ones) | vn_h1].
+//     D          = TMEM columns, read back with tcgen05.ld.32x32b (one row per thread) for the fused epilogues:
+//                  vector norms (:153), ReLU (:172), sigmoid gate (:158-163).
 // Three algebraic folds keep the per-edge GEMM work and the number of MMA <-> epilogue round trips small:
 //   (1) linearity before the gather: the s_j / s_i blocks of W_s and the V_j / V_i blocks of W_h of the FIRST message
 //       GVP act on per-node rows, so they are applied once per node (tc_node_proj_kernel) and gathered; the per-edge
 //       K of that GEMM drops from 265 to 66;
 //   (2) the gate reads the PRE-activation s' (vector_act is None, :159-162), which is linear in [s ; vn ; 1]:
-//       gate = (W_sv W_s) [s ; vn ; 1] + (W_sv b_s + b_g) rides the scalar GEMM as extra output columns;
-//   (3) Vo = W_mu Vh = (W_mu W_h) V rides the W_h GEMM as extra output columns.
-// Per tile that leaves 1 + 2 + 2 MMA batches.  Bias rows ride the GEMMs as a ones column.
+//       gate = (W_sv W_s) [s ; vn ; 1] + (W_sv b_s + b_g) rides the scalar GEMM as 16 extra output columns;
+//   (3) Vo = W_mu Vh = (W_mu W_h) V rides the W_h GEMM as 16 extra output columns.
+// Per tile that leaves 1 + 2 + 2 MMA batches (was 2 + 3 + 3).  bias rows ride the GEMMs as a ones column.
 // Aggregation: deterministic segmented sum over the sorted targets (per-tile pieces + conv_fixup_kernel).
 // Accuracy: bf16 operands -> scale-relative error ~2e-3 (north star allows <= 1e-2 with tensor cores); the fp32
 // paths (conv_reg.cu / conv.cu) remain the default -- see cgvp_set_tensor_cores().
@@ -32,82 +29,36 @@
 using namespace cgvpr;
 
 constexpr CGVP_HD inline int pad16(int x) { return (x + 15) / 16 * 16; }
-constexpr CGVP_HD inline int pad8(int x) { return (x + 7) / 8 * 8; }
-
-// where a fused column / K slot comes from
-enum { SRC_ZERO = 0, SRC_S = 1, SRC_VN = 2, SRC_ONE = 3, SRC_ES = 4, SRC_GATE = 5, SRC_VH = 6, SRC_VO = 7 };
-struct Slot { int kind, idx; };
 
 template <int NS_, int NV_, int ES_, int EV_>
 struct TcSpec {
     static constexpr int NS = NS_, NV = NV_, ES = ES_, EV = EV_, EV1 = max1(EV_);
     static constexpr int H0 = 2 * NV + EV;                       // hidden vector channels of message GVP 0
+    static constexpr int HQ = pad4(H0);
     static constexpr int SI0 = 2 * NS + ES, KSD0 = SI0 + H0, KSD1 = NS + NV;
     static constexpr int SOP = pad4(NS), VOP = pad4(NV), HP0 = pad4(H0), HP1 = pad4(NV);
-    // per-half column groups
-    static constexpr int N_S = pad16(NS), N_V = pad16(NV);
-    static constexpr int SH = N_S / 2, GH = N_V / 2, HALF = SH + GH, N_SG = 2 * HALF, N_HV = 2 * N_V;
-    static_assert(NS < N_S, "the ones column lives in a pad slot of s");
-    static_assert(HALF % 16 == 0 && SH % 8 == 0 && GH % 8 == 0, "half rows are loaded 16 columns at a time");
-    static_assert(ES % 16 == 0, "edge scalars are split evenly in 8-value chunks");
-    static constexpr int VH0 = (H0 + 1) / 2, VH1 = H0 - VH0;     // stage-0 hidden vector channels per half
-    static constexpr int VHA = pad4(VH0), VHB = pad4(VH1);       // their widths in the node tables
-    static constexpr int VS = pad8(imax(VH0, VH1 + 1));          // A-operand slots per half (the ones column sits after VH1)
-    static constexpr int ESH = ES / 2;
-    static constexpr int K_S0 = 2 * (ESH + VS), K_H = 2 * GH, K_S1 = N_SG;
-    static_assert(K_S0 % 16 == 0 && K_H % 16 == 0, "bf16 MMA K granularity");
-    static constexpr int NSG = N_SG;                             // node-projected scalar row (same order as the GEMM output)
-    static constexpr int PV_H1 = VHA + GH, PVW = VHA + GH + VHB + GH;   // node-projected vector row per plane
+    // fused scalar GEMM output row: [s' (NS -> N_S) | gate pre-activation (NV -> N_V)]
+    static constexpr int N_S = pad16(NS), N_V = pad16(NV), N_SG = N_S + N_V, N_HV = 2 * N_V;
+    static constexpr int NSG = pad4(NS + NV);                    // node-projected scalar row: [s' part | gate part]
+    static constexpr int PVW = HQ + N_V;                         // node-projected vector row per plane: [Vh | Vo]
+    static constexpr int K_S0 = pad16(ES + H0 + 1), K_H = pad16(NV), K_S1 = pad16(NS + NV + 1);
     // bf16 weight arena (bytes, [k/8][n][8] blocks)
     static constexpr int W_S0 = 0, W_ST1 = W_S0 + N_SG * K_S0 * 2;
     static constexpr int W_HV = 0, W_S = W_HV + N_HV * K_H * 2, W_STAGE = W_S + N_SG * K_S1 * 2;
     static constexpr int W_BYTES = W_ST1 + 2 * W_STAGE;
-    // fp32 side arena (floats): edge-vector columns [EV][PVW], node-projection weights
-    static constexpr int F_WHE = 0, F_WSN = pad4(EV1 * PVW), F_WVN = F_WSN + 2 * NS * NSG, F_END = F_WVN + 2 * NV * PVW;
-    static constexpr int EF = F_WSN;                             // kept in shared memory
-    // TMEM columns per group
+    // fp32 side arena (floats)
+    static constexpr int F_WHE = 0, F_WVOE = F_WHE + pad4(EV1 * HQ), F_WSN = F_WVOE + pad4(EV1 * N_V);
+    static constexpr int F_WVN = F_WSN + 2 * NS * NSG, F_END = F_WVN + 2 * NV * PVW;
+    static constexpr int EF = F_WSN;                             // per-edge extras kept in shared memory
+    // TMEM columns per warpgroup
     static constexpr int C_HV = 0, C_S = C_HV + 3 * N_HV, C_END = C_S + N_SG;
-    static_assert(C_END <= 256, "TMEM columns per group");
-    // activation tile region per group (bytes)
+    static_assert(C_END <= 256, "TMEM columns per warpgroup");
+    // activation tile region per warpgroup (bytes)
     static constexpr int A_S = 0, A_V = A_S + (K_S1 / 8) * 2048;
     static constexpr int CH = NS + 3 * NV, CHH = (CH + 1) / 2;   // message channels; reduced in two halves
     static constexpr int TILE_BYTES = imax(imax((K_S0 / 8) * 2048, A_V + 3 * (K_H / 8) * 2048), (int)align_up(CHH * 129 * 4, 16));
-    static constexpr int GRP_BYTES = TILE_BYTES + 4 * 128 * 4 + 64;   // + src/dst/eid/spare + mbarrier
-    static constexpr size_t smem_bytes() { return 1024 + (size_t)W_BYTES + EF * 4 + 2 * (size_t)GRP_BYTES + 64; }
-
-    // fused scalar output column n (also the layout of the node-projected scalar rows)
-    static constexpr CGVP_HD Slot out_s(int n) {
-        const int h = n / HALF, r = n % HALF;
-        if (r < SH) return h * SH + r < NS ? Slot{SRC_S, h * SH + r} : Slot{SRC_ZERO, 0};
-        return h * GH + (r - SH) < NV ? Slot{SRC_GATE, h * GH + (r - SH)} : Slot{SRC_ZERO, 0};
-    }
-    // K slot k of the scalar GEMM of stages >= 1: [s_h | vn_h] per half, the ones column at s index NS
-    static constexpr CGVP_HD Slot in_s1(int k) {
-        const int h = k / HALF, r = k % HALF;
-        if (r < SH) { const int i = h * SH + r; return i < NS ? Slot{SRC_S, i} : (i == NS ? Slot{SRC_ONE, 0} : Slot{SRC_ZERO, 0}); }
-        return h * GH + (r - SH) < NV ? Slot{SRC_VN, h * GH + (r - SH)} : Slot{SRC_ZERO, 0};
-    }
-    // K slot k of the scalar GEMM of stage 0: [e_s_h | vn_h (+ ones in half 1)] per half
-    static constexpr CGVP_HD Slot in_s0(int k) {
-        const int h = k / (ESH + VS), r = k % (ESH + VS);
-        if (r < ESH) return Slot{SRC_ES, h * ESH + r};
-        const int s = r - ESH;
-        if (h == 0) return s < VH0 ? Slot{SRC_VN, s} : Slot{SRC_ZERO, 0};
-        return s < VH1 ? Slot{SRC_VN, VH0 + s} : (s == VH1 ? Slot{SRC_ONE, 0} : Slot{SRC_ZERO, 0});
-    }
-    // output column n of the vector GEMM of stages >= 1: [Vh_h | Vo_h] per half
-    static constexpr CGVP_HD Slot out_hv(int n) {
-        const int h = n / (2 * GH), r = n % (2 * GH);
-        const int c = h * GH + (r < GH ? r : r - GH);
-        return c < NV ? Slot{r < GH ? SRC_VH : SRC_VO, c} : Slot{SRC_ZERO, 0};
-    }
-    // column n of a node-projected vector row (stage 0): [Vh_h0 | Vo_h0 | Vh_h1 | Vo_h1]
-    static constexpr CGVP_HD Slot out_pv(int n) {
-        if (n < VHA) return n < VH0 ? Slot{SRC_VH, n} : Slot{SRC_ZERO, 0};
-        if (n < PV_H1) return n - VHA < NV ? Slot{SRC_VO, n - VHA} : Slot{SRC_ZERO, 0};
-        if (n < PV_H1 + VHB) return n - PV_H1 < VH1 ? Slot{SRC_VH, VH0 + (n - PV_H1)} : Slot{SRC_ZERO, 0};
-        return GH + (n - PV_H1 - VHB) < NV ? Slot{SRC_VO, GH + (n - PV_H1 - VHB)} : Slot{SRC_ZERO, 0};
-    }
+    static constexpr int WG_BYTES = TILE_BYTES + 4 * 128 * 4 + 64;   // + src/dst/eid/spare + mbarrier
+    static constexpr size_t smem_bytes() { return 1024 + (size_t)W_BYTES + EF * 4 + 2 * (size_t)WG_BYTES + 64; }
     static bool matches(const CgvpConvDesc& d) {
         using G0 = GvpC<SI0, H0, NS, NV, H0, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
         using G1 = GvpC<NS, NV, NS, NV, NV, CGVP_ACT_RELU, CGVP_ACT_NONE, 1>;
@@ -155,7 +106,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void grp_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -218,28 +169,30 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 }
 
 // ---- weight pre-packing -------------------------------------------------------------------------------------------------
-// Generic fp32 packed blocks (cgvp_common.cuh) -> bf16 [k/8][n][8] blocks of the fused / permuted GEMM shapes, plus the
+// Generic fp32 packed blocks (cgvp_common.cuh) -> bf16 [k/8][n][8] blocks of the padded / fused GEMM shapes, plus the
 // fp32 side arena (node-projection weights and the edge-vector columns).
 template <class S>
 struct TcW {
     using G0 = GvpC<S::SI0, S::H0, S::NS, S::NV, S::H0, 1, 0, 1>;
     using G1 = GvpC<S::NS, S::NV, S::NS, S::NV, S::NV, 1, 0, 1>;
-    // weight from ws input row `row` (a row of ws_t; bias row = KSD) to the fused output slot `o`
+    // fused scalar weight of input row `row` (a row of ws_t, bias row = KSD) and fused output column n
     template <class G>
-    static __device__ float sg(const float* w, int row, Slot o, bool bias_row) {
-        if (o.kind == SRC_S) return w[G::O_WS_T + row * S::SOP + o.idx];
-        if (o.kind != SRC_GATE) return 0.f;
-        float acc = bias_row ? w[G::O_WSV_T + S::NS * S::VOP + o.idx] : 0.f;
-        for (int j = 0; j < S::NS; ++j) acc += w[G::O_WS_T + row * S::SOP + j] * w[G::O_WSV_T + j * S::VOP + o.idx];
+    static __device__ float sg(const float* w, int row, int n, bool bias_row) {
+        if (n < S::NS) return w[G::O_WS_T + row * S::SOP + n];
+        const int o = n - S::N_S;
+        if (o < 0 || o >= S::NV) return 0.f;
+        float acc = bias_row ? w[G::O_WSV_T + S::NS * S::VOP + o] : 0.f;
+        for (int j = 0; j < S::NS; ++j) acc += w[G::O_WS_T + row * S::SOP + j] * w[G::O_WSV_T + j * S::VOP + o];
         return acc;
     }
-    // weight from wh input channel row `crow` to the fused vector output slot `o` (Vh channel or Vo channel)
+    // fused vector weight of input channel row `crow` (a row of wh_t) and output column n: [Vh (width vw) | Vo]
     template <class G, int H, int HP>
-    static __device__ float hv(const float* w, int crow, Slot o) {
-        if (o.kind == SRC_VH) return w[G::O_WH_T + crow * HP + o.idx];
-        if (o.kind != SRC_VO) return 0.f;
+    static __device__ float hv(const float* w, int crow, int n, int vw) {
+        if (n < vw) return n < H ? w[G::O_WH_T + crow * HP + n] : 0.f;
+        const int o = n - vw;
+        if (o >= S::NV) return 0.f;
         float acc = 0.f;
-        for (int h = 0; h < H; ++h) acc += w[G::O_WH_T + crow * HP + h] * w[G::O_WV_T + h * S::VOP + o.idx];
+        for (int h = 0; h < H; ++h) acc += w[G::O_WH_T + crow * HP + h] * w[G::O_WV_T + h * S::VOP + o];
         return acc;
     }
 };
@@ -252,15 +205,19 @@ __global__ void tc_pack_kernel(const float* __restrict__ w0, const float* __rest
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < S::F_END) {                                    // ---- fp32 side arena
         float v = 0.f;
-        if (i < S::F_WSN) {
-            const int c = i / S::PVW, n = i % S::PVW;
-            if (c < S::EV) v = W::template hv<G0, S::H0, S::HP0>(w0, S::NV + c, S::out_pv(n));
+        if (i < S::F_WVOE) {
+            const int c = i / S::HQ, o = i % S::HQ;
+            if (c < S::EV) v = W::template hv<G0, S::H0, S::HP0>(w0, S::NV + c, o, S::HQ);
+        } else if (i < S::F_WSN) {
+            const int j = i - S::F_WVOE, c = j / S::N_V, o = j % S::N_V;
+            if (c < S::EV) v = W::template hv<G0, S::H0, S::HP0>(w0, S::NV + c, S::HQ + o, S::HQ);
         } else if (i < S::F_WVN) {
             const int j = i - S::F_WSN, side = j / (S::NS * S::NSG), r = j % (S::NS * S::NSG), k = r / S::NSG, n = r % S::NSG;
-            v = W::template sg<G0>(w0, side ? S::NS + S::ES + k : k, S::out_s(n), false);
+            const int row = side ? S::NS + S::ES + k : k;
+            if (n < S::NS + S::NV) v = W::template sg<G0>(w0, row, n < S::NS ? n : S::N_S + (n - S::NS), false);
         } else {
             const int j = i - S::F_WVN, side = j / (S::NV * S::PVW), r = j % (S::NV * S::PVW), c = r / S::PVW, n = r % S::PVW;
-            v = W::template hv<G0, S::H0, S::HP0>(w0, side ? S::NV + S::EV + c : c, S::out_pv(n));
+            v = W::template hv<G0, S::H0, S::HP0>(w0, side ? S::NV + S::EV + c : c, n, S::HQ);
         }
         wf[i] = v;
     }
@@ -273,31 +230,29 @@ __global__ void tc_pack_kernel(const float* __restrict__ w0, const float* __rest
         k = (j / (npad * 8)) * 8 + (j & 7);
         n = (j >> 3) % npad;
     };
-    if (byte < S::W_ST1) {                                 // GVP 0 scalar GEMM, edge part
+    if (byte < S::W_ST1) {                                 // GVP 0 scalar GEMM, edge part: [e_s ; vn ; 1]
         blk(S::W_S0, S::N_SG);
-        const Slot in = S::in_s0(k);
-        if (in.kind == SRC_ES) v = W::template sg<G0>(w0, S::NS + in.idx, S::out_s(n), false);
-        else if (in.kind == SRC_VN) v = W::template sg<G0>(w0, S::SI0 + in.idx, S::out_s(n), false);
-        else if (in.kind == SRC_ONE) v = W::template sg<G0>(w0, S::KSD0, S::out_s(n), true);
+        if (k < S::ES) v = W::template sg<G0>(w0, S::NS + k, n, false);
+        else if (k < S::ES + S::H0) v = W::template sg<G0>(w0, S::SI0 + (k - S::ES), n, false);
+        else if (k == S::ES + S::H0) v = W::template sg<G0>(w0, S::KSD0, n, true);
     } else {
         const int st = (byte - S::W_ST1) / S::W_STAGE;
         const int base = S::W_ST1 + st * S::W_STAGE;
         const float* w = st == 0 ? w1 : w2;
         if (byte - base < S::W_S) {                        // [Vh | Vo] = [W_h ; W_mu W_h] V
             blk(base + S::W_HV, S::N_HV);
-            if (k < S::NV) v = W::template hv<G1, S::NV, S::HP1>(w, k, S::out_hv(n));
+            if (k < S::NV) v = W::template hv<G1, S::NV, S::HP1>(w, k, n, S::N_V);
         } else {                                           // [s' | gate] from [s ; vn ; 1]
             blk(base + S::W_S, S::N_SG);
-            const Slot in = S::in_s1(k);
-            if (in.kind == SRC_S) v = W::template sg<G1>(w, in.idx, S::out_s(n), false);
-            else if (in.kind == SRC_VN) v = W::template sg<G1>(w, S::NS + in.idx, S::out_s(n), false);
-            else if (in.kind == SRC_ONE) v = W::template sg<G1>(w, S::KSD1, S::out_s(n), true);
+            if (k <= S::KSD1) v = W::template sg<G1>(w, k, n, k == S::KSD1);
         }
     }
     out[i] = __float2bfloat16_rn(v);
 }
 
 // ---- per-node projections of message GVP 0 (fp32) -------------------------------------------------------------------------
+//   psj[n] = Wsn[0]^T x_s[n]   psi[n] = Wsn[1]^T x_s[n]            ([s' part | gate part], width NSG)
+//   pvj[n][p] = Wvn[0]^T x_V[n][:, p]   pvi likewise                ([Vh | Vo], width PVW)
 template <class S>
 __global__ void __launch_bounds__(256) tc_node_proj_kernel(long long N, const float* __restrict__ x_s, const float* __restrict__ x_v,
                                                             const float* __restrict__ wf, float* __restrict__ psj,
@@ -369,201 +324,73 @@ __device__ __forceinline__ void add_row(const float* __restrict__ p, float* d) {
     }
 }
 
-struct GrpCtx {
-    unsigned char* tile;
-    uint64_t* bar;
-    uint32_t tm, tm_grp, w0s;
-    int grp, row;
-    bool leader;
-    const float* ef;
-};
-
-// One MMA batch of a group: publish the A tiles, let the leader issue, wait for completion.
+// One MMA batch of a warpgroup: publish the A tiles, let the leader issue, wait for completion.
 #define TC_BATCH_BEGIN()            \
     fence_proxy_async();            \
     tc_fence_before();              \
-    grp_sync(g.grp);                \
-    if (g.leader) {                 \
+    wg_sync(wg);                    \
+    if (leader) {                   \
         tc_fence_after();
 #define TC_BATCH_COMMIT()           \
-        mma_commit(g.bar);          \
+        mma_commit(bar);            \
     }
 #define TC_BATCH_WAIT()             \
-    mbar_wait(g.bar, phase);        \
+    mbar_wait(bar, phase);          \
     phase ^= 1;                     \
     tc_fence_after();
 
-// this half's [s'_h | gate_h] (HALF columns) from TMEM (+ optional addend already in sg), vo in registers -> outputs
-template <class S, int H, bool RELU, bool ADD>
-__device__ __forceinline__ void finish_stage(uint32_t tm, float (&sg)[S::HALF], float (&vo)[3][S::GH]) {
+// [s' | gate] in TMEM (+ optional addend already in sg) and vo in registers -> (s_out, V_out)
+template <class S, bool RELU, bool ADD>
+__device__ __forceinline__ void finish_stage(uint32_t tm, float (&sg)[S::N_SG], float (&vo)[3][S::N_V]) {
     if (ADD) {
-        float d[S::HALF];
+        constexpr int NB = S::N_SG / 16, B0 = (NB + 1) / 2;
+        float d0[16 * B0], d1[16 * (NB - B0 > 0 ? NB - B0 : 1)];
 #pragma unroll
-        for (int c = 0; c < S::HALF / 16; ++c) tmem_ld16(tm + S::C_S + H * S::HALF + 16 * c, d + 16 * c);
-        tmem_ld_wait(d);
+        for (int c = 0; c < B0; ++c) tmem_ld16(tm + S::C_S + 16 * c, d0 + 16 * c);
 #pragma unroll
-        for (int j = 0; j < S::HALF; ++j) sg[j] += d[j];
+        for (int c = B0; c < NB; ++c) tmem_ld16(tm + S::C_S + 16 * c, d1 + 16 * (c - B0));
+        tmem_ld_wait(d0); tmem_ld_wait(d1);
+#pragma unroll
+        for (int j = 0; j < 16 * B0; ++j) sg[j] += d0[j];
+#pragma unroll
+        for (int j = 16 * B0; j < 16 * NB; ++j) sg[j] += d1[j - 16 * B0];
     } else {
 #pragma unroll
-        for (int c = 0; c < S::HALF / 16; ++c) tmem_ld16(tm + S::C_S + H * S::HALF + 16 * c, sg + 16 * c);
+        for (int c = 0; c < S::N_SG / 16; ++c) tmem_ld16(tm + S::C_S + 16 * c, sg + 16 * c);
         tmem_ld_wait(sg);
     }
 #pragma unroll
-    for (int c = 0; c < S::GH; ++c) {
-        const float gt = fast_sigmoid(sg[S::SH + c]);                                    // :158-163
+    for (int c = 0; c < S::NV; ++c) {
+        const float g = fast_sigmoid(sg[S::N_S + c]);                                   // :158-163
 #pragma unroll
-        for (int p = 0; p < 3; ++p) vo[p][c] *= gt;
+        for (int p = 0; p < 3; ++p) vo[p][c] *= g;
     }
     if (RELU) {
 #pragma unroll
-        for (int k = 0; k < S::SH; ++k) sg[k] = fmaxf(sg[k], 0.f);                       // :172-173
+        for (int k = 0; k < S::NS; ++k) sg[k] = fmaxf(sg[k], 0.f);                       // :172-173
     }
-}
-
-// Everything one half-row thread does for one tile up to (and including) writing its message channels for the reduce.
-template <class S, int H>
-__device__ __forceinline__ void tile_messages(const TcArgs& a, const GrpCtx& g, uint32_t& phase, int src, int dst, long long eid,
-                                              float (&sg)[S::HALF], float (&v)[3][S::GH]) {
-    constexpr int VHW = H == 0 ? S::VHA : S::VHB;          // this half's Vh width in the node tables
-    constexpr int VHN = H == 0 ? S::VH0 : S::VH1;          // ... and its real channel count
-    constexpr int PVO = H == 0 ? 0 : S::PV_H1;             // offset of this half inside a node-projected vector row
-    unsigned char* tile = g.tile;
-    const int row = g.row;
-    // ================= message GVP 0 =================
-    {
-        float vh[3][VHW];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const float* pj = a.pvj + ((long long)src * 3 + q) * S::PVW + PVO;
-            const float* pi = a.pvi + ((long long)dst * 3 + q) * S::PVW + PVO;
-            ld_row<VHW>(pj, vh[q]);
-            add_row<VHW>(pi, vh[q]);
-            ld_row<S::GH>(pj + VHW, v[q]);
-            add_row<S::GH>(pi + VHW, v[q]);
-        }
-        if constexpr (S::EV > 0) {
-#pragma unroll
-            for (int c = 0; c < S::EV; ++c) {
-                const float* we = g.ef + S::F_WHE + c * S::PVW + PVO;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float e = __ldg(a.e_v + (eid * S::EV + c) * 3 + q);
-#pragma unroll
-                    for (int o = 0; o < VHN; ++o) vh[q][o] = fmaf(e, we[o], vh[q][o]);
-#pragma unroll
-                    for (int o = 0; o < S::GH; ++o) v[q][o] = fmaf(e, we[VHW + o], v[q][o]);
-                }
-            }
-        }
-        float es[S::ESH];
-        ld_row<S::ESH>(a.e_s + eid * S::ES + H * S::ESH, es);
-        constexpr int C0 = H * (S::ESH + S::VS) / 8;       // first chunk of this half
-#pragma unroll
-        for (int c = 0; c < (S::ESH + S::VS) / 8; ++c) {
-            float q8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = 8 * c + j;
-                if (r < S::ESH) q8[j] = es[r < S::ESH ? r : 0];
-                else {
-                    const int s_ = r - S::ESH;
-                    if (s_ < VHN) {
-                        const int o = (s_ >= 0 && s_ < VHN) ? s_ : 0;
-                        q8[j] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));   // :153
-                    } else q8[j] = (H == 1 && s_ == S::VH1) ? 1.f : 0.f;
-                }
-            }
-            put8(tile + S::A_S, C0 + c, row, q8);
-        }
-        TC_BATCH_BEGIN()
-            issue_gemm<S::N_SG, S::K_S0>(g.tm_grp + S::C_S, smem_u32(tile + S::A_S), g.w0s + S::W_S0);
-        TC_BATCH_COMMIT()
-        ld_row<S::HALF>(a.psj + (long long)src * S::NSG + H * S::HALF, sg);     // node-projected part of [s' | gate]
-        add_row<S::HALF>(a.psi + (long long)dst * S::NSG + H * S::HALF, sg);
-        TC_BATCH_WAIT()
-        finish_stage<S, H, true, true>(g.tm, sg, v);
-    }
-    // ================= message GVPs 1 and 2 =================
-#pragma unroll
-    for (int st = 0; st < 2; ++st) {
-        const uint32_t wst = g.w0s + S::W_ST1 + st * S::W_STAGE;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) put8(tile + S::A_V + q * (S::K_H / 8) * 2048, H, row, v[q]);
-        TC_BATCH_BEGIN()
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                issue_gemm<S::N_HV, S::K_H>(g.tm_grp + S::C_HV + q * S::N_HV, smem_u32(tile + S::A_V + q * (S::K_H / 8) * 2048), wst + S::W_HV);
-        TC_BATCH_COMMIT()
-        // meanwhile: this half's scalar slots of the next A operand (s, the ones column, zero padding)
-#pragma unroll
-        for (int c = 0; c < S::SH / 8; ++c) {
-            float q8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int i = H * S::SH + 8 * c + j;
-                q8[j] = i < S::NS ? sg[8 * c + j] : (i == S::NS ? 1.f : 0.f);
-            }
-            put8(tile + S::A_S, H * (S::HALF / 8) + c, row, q8);
-        }
-        TC_BATCH_WAIT()
-        {
-            float hv[3][2 * S::GH];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) tmem_ld16(g.tm + S::C_HV + q * S::N_HV + H * 2 * S::GH, hv[q]);
-            tmem_ld_wait(hv[0]); tmem_ld_wait(hv[1]); tmem_ld_wait(hv[2]);
-            float vn[S::GH];
-#pragma unroll
-            for (int o = 0; o < S::GH; ++o) {
-                vn[o] = fast_sqrt(fmaxf(hv[0][o] * hv[0][o] + hv[1][o] * hv[1][o] + hv[2][o] * hv[2][o], CGVP_EPS));     // :153
-#pragma unroll
-                for (int q = 0; q < 3; ++q) v[q][o] = hv[q][S::GH + o];
-            }
-            put8(tile + S::A_S, H * (S::HALF / 8) + S::SH / 8, row, vn);
-        }
-        TC_BATCH_BEGIN()
-            issue_gemm<S::N_SG, S::K_S1>(g.tm_grp + S::C_S, smem_u32(tile + S::A_S), wst + S::W_S);
-        TC_BATCH_COMMIT()
-        TC_BATCH_WAIT()
-        if (st == 0) finish_stage<S, H, true, false>(g.tm, sg, v);
-        else finish_stage<S, H, false, false>(g.tm, sg, v);
-    }
-}
-
-// write this thread's message channels that fall into [ch0, ch0 + CHH) into M[ch - ch0][row]
-template <class S, int H>
-__device__ __forceinline__ void stage_channels(float* M, int row, int ch0, const float (&sg)[S::HALF], const float (&v)[3][S::GH]) {
-#pragma unroll
-    for (int j = 0; j < S::SH; ++j) {
-        const int ch = H * S::SH + j;
-        if (ch < S::NS && ch >= ch0 && ch < ch0 + S::CHH) M[(ch - ch0) * 129 + row] = sg[j];
-    }
-#pragma unroll
-    for (int c = 0; c < S::GH; ++c)
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const int cc = H * S::GH + c, ch = S::NS + 3 * cc + p;
-            if (cc < S::NV && ch >= ch0 && ch < ch0 + S::CHH) M[(ch - ch0) * 129 + row] = v[p][c];
-        }
 }
 
 template <class S>
-__global__ void __launch_bounds__(512, 1) conv_tc_fwd_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(256, 1) conv_tc_fwd_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* wsm = smem;
-    float* ef = reinterpret_cast<float*>(smem + S::W_BYTES);
-    unsigned char* gbase = smem + S::W_BYTES + S::EF * 4;
-    const int tid = threadIdx.x, grp = tid >> 8, u = tid & 255, row = u & 127, half = u >> 7, warp = tid >> 5;
-    unsigned char* tile = gbase + grp * S::GRP_BYTES;
-    int* idst = reinterpret_cast<int*>(tile + S::TILE_BYTES);
+    float* ef = reinterpret_cast<float*>(smem + S::W_BYTES);           // whe | wvoe
+    unsigned char* wgbase = smem + S::W_BYTES + S::EF * 4;
+    const int tid = threadIdx.x, wg = tid >> 7, row = tid & 127, warp = tid >> 5;
+    unsigned char* tile = wgbase + wg * S::WG_BYTES;
+    int* isrc = reinterpret_cast<int*>(tile + S::TILE_BYTES);
+    int* idst = isrc + 128;
+    int* ieid = idst + 128;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tile + S::TILE_BYTES + 4 * 128 * 4);
-    uint64_t* wbar = reinterpret_cast<uint64_t*>(gbase + 2 * S::GRP_BYTES);
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(wgbase + 2 * S::WG_BYTES);
     uint32_t* slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
     if (tid == 0) {
         mbar_init(wbar, 1);
-        mbar_init(reinterpret_cast<uint64_t*>(gbase + S::TILE_BYTES + 4 * 128 * 4), 1);
-        mbar_init(reinterpret_cast<uint64_t*>(gbase + S::GRP_BYTES + S::TILE_BYTES + 4 * 128 * 4), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(wgbase + S::TILE_BYTES + 4 * 128 * 4), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(wgbase + S::WG_BYTES + S::TILE_BYTES + 4 * 128 * 4), 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(slot, 512);
@@ -577,41 +404,174 @@ __global__ void __launch_bounds__(512, 1) conv_tc_fwd_kernel(const __grid_consta
         for (int off = 0; off < S::W_BYTES; off += CHUNK)
             bulk_g2s(wsm + off, a.wtc + off, (uint32_t)(S::W_BYTES - off < CHUNK ? S::W_BYTES - off : CHUNK), wbar);
     }
-    GrpCtx g;
-    g.tile = tile; g.bar = bar; g.grp = grp; g.row = row; g.leader = u == 0; g.ef = ef;
-    g.tm_grp = *slot + (uint32_t)(grp * 256);                                   // MMA destination (lane 0)
-    g.tm = g.tm_grp + ((uint32_t)((warp & 3) * 32) << 16);                       // this thread's lane quarter
-    g.w0s = smem_u32(wsm);
+    const uint32_t tm_wg = *slot + (uint32_t)(wg * 256);                          // MMA destination (lane 0)
+    const uint32_t tm = tm_wg + ((uint32_t)((warp & 3) * 32) << 16);               // this thread's lane
     mbar_wait(wbar, 0);
     uint32_t phase = 0;
+    const bool leader = row == 0;
+    const uint32_t w0s = smem_u32(wsm);
+    const float* whe = ef + S::F_WHE;
+    const float* wvoe = ef + S::F_WVOE;
 
-    for (int t = blockIdx.x * 2 + grp; t < a.ntiles; t += gridDim.x * 2) {
+    for (int t = blockIdx.x * 2 + wg; t < a.ntiles; t += gridDim.x * 2) {
         const long long p0 = (long long)t * 128;
         const int rv = (int)min(128LL, a.E - p0);
         const long long p = row < rv ? p0 + row : p0;       // idle rows replay the first edge (never stored)
         const int src = __ldg(a.src + p), dst = __ldg(a.dst + p);
         const long long eid = a.edge_sorted ? p : (long long)__ldg(a.perm + p);
-        grp_sync(grp);                                      // previous tile's reduce is done with the tile region / index array
-        if (half == 0) idst[row] = dst;
+        wg_sync(wg);                                        // previous tile's reduce is done with the tile region / index arrays
+        isrc[row] = src; idst[row] = dst; ieid[row] = (int)eid;
 
-        float sg[S::HALF], v[3][S::GH];
-        if (half == 0) tile_messages<S, 0>(a, g, phase, src, dst, eid, sg, v);
-        else tile_messages<S, 1>(a, g, phase, src, dst, eid, sg, v);
-
+        float sg[S::N_SG], v[3][S::N_V];
+        // ================= message GVP 0 =================
+        {
+            // [Vh | Vo] = node projections + edge-vector columns                                                   :152,:156
+            float vh[3][S::HQ];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float* pj = a.pvj + ((long long)src * 3 + q) * S::PVW;
+                const float* pi = a.pvi + ((long long)dst * 3 + q) * S::PVW;
+                ld_row<S::HQ>(pj, vh[q]);
+                add_row<S::HQ>(pi, vh[q]);
+                ld_row<S::N_V>(pj + S::HQ, v[q]);
+                add_row<S::N_V>(pi + S::HQ, v[q]);
+            }
+            if constexpr (S::EV > 0) {
+#pragma unroll
+                for (int c = 0; c < S::EV; ++c) {
+                    float e3[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) e3[q] = __ldg(a.e_v + (eid * S::EV + c) * 3 + q);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                        for (int o = 0; o < S::H0; ++o) vh[q][o] = fmaf(e3[q], whe[c * S::HQ + o], vh[q][o]);
+#pragma unroll
+                        for (int o = 0; o < S::NV; ++o) v[q][o] = fmaf(e3[q], wvoe[c * S::N_V + o], v[q][o]);
+                    }
+                }
+            }
+            // A operand [e_s ; vn ; 1]
+            float es[S::ES];
+            ld_row<S::ES>(a.e_s + eid * S::ES, es);
+#pragma unroll
+            for (int c = 0; c < S::K_S0 / 8; ++c) {
+                float q8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 8 * c + j;
+                    if (k < S::ES) q8[j] = es[k < S::ES ? k : 0];
+                    else if (k < S::ES + S::H0) {
+                        const int o = (k - S::ES >= 0 && k - S::ES < S::H0) ? k - S::ES : 0;
+                        q8[j] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));   // :153
+                    } else q8[j] = k == S::ES + S::H0 ? 1.f : 0.f;
+                }
+                put8(tile + S::A_S, c, row, q8);
+            }
+            TC_BATCH_BEGIN()
+                issue_gemm<S::N_SG, S::K_S0>(tm_wg + S::C_S, smem_u32(tile + S::A_S), w0s + S::W_S0);
+            TC_BATCH_COMMIT()
+            // while the tensor pipe works: the node-projected part of [s' | gate]
+            {
+                float* g = sg;
+                ld_row<S::NS>(a.psj + (long long)src * S::NSG, g);
+                add_row<S::NS>(a.psi + (long long)dst * S::NSG, g);
+#pragma unroll
+                for (int k = S::NS; k < S::N_S; ++k) sg[k] = 0.f;
+                ld_row<S::N_V>(a.psj + (long long)src * S::NSG + S::NS, g + S::N_S);
+                add_row<S::N_V>(a.psi + (long long)dst * S::NSG + S::NS, g + S::N_S);
+            }
+            TC_BATCH_WAIT()
+            finish_stage<S, true, true>(tm, sg, v);
+        }
+        // ================= message GVPs 1 and 2 =================
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+            const uint32_t wst = w0s + S::W_ST1 + st * S::W_STAGE;
+            // [Vh | Vo] = [W_h ; W_mu W_h] V                                                                       :152,:156
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int c = 0; c < S::K_H / 8; ++c) {
+                    float q8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int o = 8 * c + j; q8[j] = o < S::NV ? v[q][o < S::NV ? o : 0] : 0.f; }
+                    put8(tile + S::A_V + q * (S::K_H / 8) * 2048, c, row, q8);
+                }
+            TC_BATCH_BEGIN()
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    issue_gemm<S::N_HV, S::K_H>(tm_wg + S::C_HV + q * S::N_HV, smem_u32(tile + S::A_V + q * (S::K_H / 8) * 2048), wst + S::W_HV);
+            TC_BATCH_COMMIT()
+            // meanwhile: the scalar part of the next A operand
+#pragma unroll
+            for (int c = 0; c < S::NS / 8; ++c) {
+                float q8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q8[j] = sg[8 * c + j];
+                put8(tile + S::A_S, c, row, q8);
+            }
+            TC_BATCH_WAIT()
+            float vn[S::N_V];
+            {
+                float vh[3][S::N_V];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                    for (int c = 0; c < S::N_V / 16; ++c) {
+                        tmem_ld16(tm + S::C_HV + q * S::N_HV + 16 * c, vh[q] + 16 * c);
+                        tmem_ld16(tm + S::C_HV + q * S::N_HV + S::N_V + 16 * c, v[q] + 16 * c);
+                    }
+                }
+                tmem_ld_wait(vh[0]); tmem_ld_wait(vh[1]); tmem_ld_wait(vh[2]);
+                tmem_ld_wait(v[0]); tmem_ld_wait(v[1]); tmem_ld_wait(v[2]);
+#pragma unroll
+                for (int o = 0; o < S::N_V; ++o)
+                    vn[o] = fast_sqrt(fmaxf(vh[0][o] * vh[0][o] + vh[1][o] * vh[1][o] + vh[2][o] * vh[2][o], CGVP_EPS));     // :153
+            }
+            // rest of [s ; vn ; 1]
+#pragma unroll
+            for (int c = S::NS / 8; c < S::K_S1 / 8; ++c) {
+                float q8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 8 * c + j;
+                    if (k < S::NS) q8[j] = sg[k < S::NS ? k : 0];
+                    else if (k < S::NS + S::NV) q8[j] = vn[(k - S::NS >= 0 && k - S::NS < S::NV) ? k - S::NS : 0];
+                    else q8[j] = k == S::NS + S::NV ? 1.f : 0.f;
+                }
+                put8(tile + S::A_S, c, row, q8);
+            }
+            TC_BATCH_BEGIN()
+                issue_gemm<S::N_SG, S::K_S1>(tm_wg + S::C_S, smem_u32(tile + S::A_S), wst + S::W_S);
+            TC_BATCH_COMMIT()
+            TC_BATCH_WAIT()
+            if (st == 0) finish_stage<S, true, false>(tm, sg, v);
+            else finish_stage<S, false, false>(tm, sg, v);
+        }
         // ================= aggregation: segmented sum over the sorted targets, two channel halves =================
+        tc_fence_before();
         float* M = reinterpret_cast<float*>(tile);
         const int n_first = idst[0], n_last = idst[rv - 1];
         const long long p1 = p0 + rv;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            grp_sync(grp);                                  // tile region free (MMAs done; previous pass consumed)
-            const int ch0 = pass * S::CHH;
-            if (half == 0) stage_channels<S, 0>(M, row, ch0, sg, v);
-            else stage_channels<S, 1>(M, row, ch0, sg, v);
-            grp_sync(grp);
+        for (int half = 0; half < 2; ++half) {
+            wg_sync(wg);                                    // tile region free (MMAs done; previous half consumed)
+            const int ch0 = half * S::CHH;
+#pragma unroll
+            for (int c = 0; c < S::CHH; ++c) {
+                const int ch = ch0 + c;
+                if (ch < S::CH) {
+                    float val;
+                    if (ch < S::NS) val = sg[ch < S::NS ? ch : 0];
+                    else { const int j = ch - S::NS >= 0 ? ch - S::NS : 0; val = v[j % 3][(j / 3) < S::NV ? j / 3 : 0]; }
+                    M[c * 129 + row] = val;
+                }
+            }
+            wg_sync(wg);
             const int span = n_last - n_first + 1;
             const int nch = min(S::CHH, S::CH - ch0);
-            for (int i = u; i < span * nch; i += 256) {
+            for (int i = row; i < span * nch; i += 128) {
                 const int n = n_first + i / nch, c = i % nch, ch = ch0 + c;
                 const long long ra_ = __ldg(a.rowptr + n), rb_ = __ldg(a.rowptr + n + 1);
                 const int ra = (int)(max(ra_, p0) - p0), rb = (int)(min(rb_, p1) - p0);
@@ -693,7 +653,7 @@ int conv_fwd_tc(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(conv_tc_fwd_kernel)");
     const int grid = (int)min((long long)cdiv64(ntiles, 2), (long long)sms);
     cgvp_prof_begin(CGVP_K_CONV_FWD, st);
-    conv_tc_fwd_kernel<S><<<grid, 512, smem, st>>>(a);
+    conv_tc_fwd_kernel<S><<<grid, 256, smem, st>>>(a);
     cgvp_prof_end(CGVP_K_CONV_FWD, st);
     conv_fixup_kernel<<<(unsigned)cdiv64(N * S::CH, 256), 256, 0, st>>>(N, S::CH, S::NS, plan->rowptr, a.mean, 7, part_head, part_tail, out_s, out_v);
     e = cudaGetLastError();
