@@ -33,6 +33,9 @@ struct FeatK {
     const int64_t* row_offsets;
     int64_t *ei, E;
     float *es, *ev;
+    const float* pe;      // [2 * max_len - 1][16] positional encodings by (dst - src) + max_len - 1, or NULL
+    int64_t max_len;
+    int cache_rows;       // shared-memory distance cache (doubles per warp), 0 = recompute
 };
 
 __device__ __forceinline__ double ca_distance(const float* __restrict__ ca, int64_t i, int64_t j) {
@@ -83,42 +86,92 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_count_kernel(const FeatK K)
     if (blockIdx.x == 0 && threadIdx.x == 0) K.deg[K.N] = 0;
 }
 
-// ---- phase 2: write edges and features -----------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_edge(const FeatK& K, int64_t e, int64_t i, int64_t j, double d, int lane) {
-    // 32 lanes = 32 scalar features of this edge: coalesced 128-byte row
-    float feat;
-    if (lane < 16) {
-        const double t = (d - c_rbf_mu[lane]) / 1.25;                       // (d - mu) / D_step            :237
-        feat = (float)exp(-(t * t));
-    } else {
-        const double ang = (double)(j - i) * c_pe_freq[lane & 7];            // (dst idx - src idx) * freq   :253,:382
-        feat = (float)(lane < 24 ? cos(ang) : sin(ang));
-    }
-    K.es[e * 32 + lane] = feat;
-    if (lane < 3) {
-        const float x = __fsub_rn(K.ca[3 * i], K.ca[3 * j]), y = __fsub_rn(K.ca[3 * i + 1], K.ca[3 * j + 1]),
-                    z = __fsub_rn(K.ca[3 * i + 2], K.ca[3 * j + 2]);                                    // :244
-        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-        const float c = lane == 0 ? x : (lane == 1 ? y : z);
-        K.ev[e * 3 + lane] = nrm != 0.f ? __fdiv_rn(c, nrm) : 0.f;                                       // :360-365
-    }
-    if (lane == 0) { K.ei[e] = i; K.ei[K.E + e] = j; }
+// positional encodings depend on (dst - src) only: [cos(delta f_0..7) ; sin(delta f_0..7)], fp64 then cast  (:368-385)
+__global__ void feat_pe_kernel(int64_t max_len, float* __restrict__ pe) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (2 * max_len - 1) * 16) return;
+    const int64_t delta = i / 16 - (max_len - 1);
+    const int f = (int)(i % 16);
+    const double ang = (double)delta * c_pe_freq[f & 7];
+    pe[i] = (float)(f < 8 ? cos(ang) : sin(ang));
 }
 
-__device__ __forceinline__ void emit_chunk(const FeatK& K, unsigned mask, int64_t& e, int64_t i, int64_t j, double d, int lane) {
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t jj = __shfl_sync(0xffffffffu, j, src);
-        const double dd = __shfl_sync(0xffffffffu, d, src);
-        emit_edge(K, e, i, jj, dd, lane);
-        ++e;
+// ---- phase 2: write edges and features -----------------------------------------------------------------------------------
+// One LANE per edge: the 16 fp64 exponentials of an edge's RBF row are independent (ILP), and up to 32 edges of the
+// row are in flight per warp.  (A lane-per-feature layout serialises the edges of a row behind the ~500-cycle latency
+// of one fp64 exp.)
+__device__ __forceinline__ void emit_edge_lane(const FeatK& K, int64_t e, int64_t i, int64_t j, double d) {
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const double t = (d - c_rbf_mu[k]) / 1.25;                           // (d - mu) / D_step            :237
+        f[k] = (float)exp(-(t * t));
     }
+    if (K.pe) {                                                              // tabulated with the same fp64 formula
+        const float4* row = reinterpret_cast<const float4*>(K.pe + ((j - i) + K.max_len - 1) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 t = __ldg(row + q);
+            f[16 + 4 * q] = t.x; f[17 + 4 * q] = t.y; f[18 + 4 * q] = t.z; f[19 + 4 * q] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double ang = (double)(j - i) * c_pe_freq[k];               // (dst idx - src idx) * freq   :253,:382
+            f[16 + k] = (float)cos(ang);
+            f[24 + k] = (float)sin(ang);
+        }
+    }
+    float4* es4 = reinterpret_cast<float4*>(K.es + e * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) es4[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    const float x = __fsub_rn(K.ca[3 * i], K.ca[3 * j]), y = __fsub_rn(K.ca[3 * i + 1], K.ca[3 * j + 1]),
+                z = __fsub_rn(K.ca[3 * i + 2], K.ca[3 * j + 2]);                                        // :244
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    K.ev[e * 3] = nrm != 0.f ? __fdiv_rn(x, nrm) : 0.f;                                                  // :360-365
+    K.ev[e * 3 + 1] = nrm != 0.f ? __fdiv_rn(y, nrm) : 0.f;
+    K.ev[e * 3 + 2] = nrm != 0.f ? __fdiv_rn(z, nrm) : 0.f;
+    K.ei[e] = i;
+    K.ei[K.E + e] = j;
+}
+
+// per-warp list of kept (column, distance) pairs, flushed 32 edges at a time in column order
+struct EdgeList {
+    int64_t* j;       // [64]
+    double* d;        // [64]
+    int cnt;
+};
+__device__ __forceinline__ void list_flush(const FeatK& K, EdgeList& L, int64_t& e, int64_t i, int lane, int n) {
+    if (lane < n) emit_edge_lane(K, e + lane, i, L.j[lane], L.d[lane]);
+    e += n;
+    __syncwarp();
+    if (L.cnt > n) {                                       // move the tail (< 32 entries) to the front
+        const bool mv = lane < L.cnt - n;
+        int64_t tj = 0; double td = 0.0;
+        if (mv) { tj = L.j[n + lane]; td = L.d[n + lane]; }
+        __syncwarp();
+        if (mv) { L.j[lane] = tj; L.d[lane] = td; }
+    }
+    L.cnt -= n;
+    __syncwarp();
+}
+__device__ __forceinline__ void emit_chunk(const FeatK& K, EdgeList& L, unsigned mask, int64_t& e, int64_t i, int64_t j, double d, int lane) {
+    if (mask >> lane & 1u) {
+        const int pos = L.cnt + __popc(mask & ((1u << lane) - 1u));
+        L.j[pos] = j; L.d[pos] = d;
+    }
+    L.cnt += __popc(mask);
+    __syncwarp();
+    if (L.cnt >= 32) list_flush(K, L, e, i, lane, 32);
 }
 
 __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) {
     __shared__ int hist[FEAT_WARPS][256];
+    __shared__ int64_t list_j[FEAT_WARPS][64];
+    __shared__ double list_d[FEAT_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    EdgeList L;
+    L.j = list_j[wib]; L.d = list_d[wib]; L.cnt = 0;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < K.N; i += nwarps) {
@@ -133,13 +186,24 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) 
                 double d = 0.0;
                 bool keep = false;
                 if (j < hi && (K.keep_self || j != i)) { d = ca_distance(K.ca, i, j); keep = d <= K.thresh; }
-                emit_chunk(K, __ballot_sync(0xffffffffu, keep), e, i, j, d, lane);
+                emit_chunk(K, L, __ballot_sync(0xffffffffu, keep), e, i, j, d, lane);
             }
+            if (L.cnt > 0) list_flush(K, L, e, i, lane, L.cnt);
             continue;
         }
         // k nearest: radix-select the k-th smallest distance (fp64 bit pattern of a non-negative double is monotone),
         // then keep d < T and the first (k - #{d < T}) ties in column order  (np.argsort(...)[:, :k], :319)
         const int kk = (int)(e_end - e);
+        // fp64 distances of this row, computed ONCE into the warp's shared-memory cache (excluded self = +inf)
+        extern __shared__ __align__(16) unsigned long long dcache[];
+        unsigned long long* drow = dcache + (size_t)wib * K.cache_rows;
+        const bool cached = K.cache_rows >= n;
+        if (cached) {
+            for (int64_t j = lo + lane; j < hi; j += 32)
+                drow[j - lo] = (K.keep_self || j != i) ? (unsigned long long)__double_as_longlong(ca_distance(K.ca, i, j))
+                                                       : 0x7ff0000000000000ull;
+            __syncwarp();
+        }
         unsigned long long prefix = 0ull, pmask = 0ull;
         int remaining = kk;
         for (int shift = 56; shift >= 0; shift -= 8) {
@@ -148,7 +212,8 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) 
             for (int64_t j0 = lo; j0 < hi; j0 += 32) {
                 const int64_t j = j0 + lane;
                 if (j < hi && (K.keep_self || j != i)) {
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(ca_distance(K.ca, i, j));
+                    const unsigned long long key = cached ? drow[j - lo]
+                                                          : (unsigned long long)__double_as_longlong(ca_distance(K.ca, i, j));
                     if ((key & pmask) == prefix) atomicAdd(&hist[wib][(int)((key >> shift) & 255ull)], 1);
                 }
             }
@@ -174,6 +239,7 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) 
             prefix |= (unsigned long long)bin << shift;
             pmask |= 255ull << shift;
             __syncwarp();
+            // early exit: exactly `remaining` keys share the prefix -> every one of them is taken, T is irrelevant below it
         }
         const double T = __longlong_as_double((long long)prefix);
         int ties_left = remaining;             // how many entries equal to T are still to be taken
@@ -181,13 +247,18 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) 
             const int64_t j = j0 + lane;
             double d = 0.0;
             bool lt = false, eq = false;
-            if (j < hi && (K.keep_self || j != i)) { d = ca_distance(K.ca, i, j); lt = d < T; eq = d == T; }
+            if (j < hi && (K.keep_self || j != i)) {
+                d = cached ? __longlong_as_double((long long)drow[j - lo]) : ca_distance(K.ca, i, j);
+                lt = d < T; eq = d == T;
+            }
             const unsigned eqm = __ballot_sync(0xffffffffu, eq);
             const bool take_eq = eq && __popc(eqm & ((1u << lane) - 1u)) < ties_left;
             const unsigned tkm = __ballot_sync(0xffffffffu, take_eq);
             ties_left -= __popc(tkm);
-            emit_chunk(K, __ballot_sync(0xffffffffu, lt) | tkm, e, i, j, d, lane);
+            emit_chunk(K, L, __ballot_sync(0xffffffffu, lt) | tkm, e, i, j, d, lane);
         }
+        if (L.cnt > 0) list_flush(K, L, e, i, lane, L.cnt);
+        __syncwarp();
     }
 }
 
@@ -199,7 +270,9 @@ static size_t scan_bytes(int64_t n) {
 
 extern "C" int64_t cgvp_featurize_workspace_bytes(int64_t num_nodes, int64_t max_protein_len) {
     if (num_nodes < 0 || num_nodes >= ((int64_t)1 << 31) - 1) return -1;
-    return align_up((num_nodes + 1) * 4, 256) + (int64_t)align_up((int64_t)scan_bytes(num_nodes + 1), 256) + 256;
+    const int64_t ml = max_protein_len > 0 ? max_protein_len : 1;
+    return align_up((num_nodes + 1) * 4, 256) + (int64_t)align_up((int64_t)scan_bytes(num_nodes + 1), 256) +
+           align_up((2 * ml - 1) * 16 * 4, 256) + 256;
 }
 
 static int feat_checks(const float* ca, const int64_t* ptr, int64_t B, int64_t N, int32_t type) {
@@ -252,8 +325,26 @@ extern "C" int32_t cgvp_featurize_fill(const float* ca, const int64_t* ptr, int6
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
     int64_t blocks = cdiv64(num_nodes, FEAT_WARPS);
     if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ml = max_protein_len > 0 ? max_protein_len : 1;
+    const int64_t need = cgvp_featurize_workspace_bytes(num_nodes, max_protein_len);
+    if (ws && ws_bytes >= need) {          // positional-encoding table behind the count phase's scratch
+        float* pe = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((num_nodes + 1) * 4, 256) +
+                                             (int64_t)align_up((int64_t)scan_bytes(num_nodes + 1), 256));
+        feat_pe_kernel<<<(int)cdiv64((2 * ml - 1) * 16, 256), 256, 0, st>>>(ml, pe);
+        CGVP_LAUNCH_CHECK("feat_pe_kernel");
+        K.pe = pe; K.max_len = ml;
+    }
+    size_t smem = 0;
+    if (thresh_type != 0 && (size_t)FEAT_WARPS * ml * 8 <= 160 * 1024) {   // kNN: cache one row of fp64 distances per warp
+        K.cache_rows = (int)ml;
+        smem = (size_t)FEAT_WARPS * ml * 8;
+        CGVP_CUDA(cudaFuncSetAttribute(feat_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t per_sm = (int64_t)(200 * 1024) / (int64_t)(smem + 5 * 1024);
+        if (blocks > (int64_t)sms * (per_sm > 0 ? per_sm : 1) * 4) blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1) * 4;
+    }
     cgvp_prof_begin(CGVP_K_FEATURIZE, (cudaStream_t)stream);
-    feat_fill_kernel<<<(int)blocks, FEAT_THREADS, 0, (cudaStream_t)stream>>>(K);
+    feat_fill_kernel<<<(int)blocks, FEAT_THREADS, smem, (cudaStream_t)stream>>>(K);
     cgvp_prof_end(CGVP_K_FEATURIZE, (cudaStream_t)stream);
     CGVP_LAUNCH_CHECK("feat_fill_kernel");
     return 0;

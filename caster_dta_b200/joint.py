@@ -242,7 +242,12 @@ class JointGNN(nn.Module):
         pg, mg = dict(protein_graph_data), dict(molecule_graph_data)
         hints_p = {k: pg.pop(k, None) for k in ("num_graphs", "max_nodes")}
         hints_m = {k: mg.pop(k, None) for k in ("num_graphs", "max_nodes")}
-        res = self._stack(self.protein_gnn(**pg), self.residue_lins, self.residue_norms)
+        # `protein_embed`: residue embeddings computed earlier for the same protein(s) -- the encoder
+        # output depends on the protein only, so an inference sweep over many ligands per protein can reuse it
+        embed = pg.pop("protein_embed", None)
+        if embed is None:
+            embed = self.protein_gnn(**pg)
+        res = self._stack(embed, self.residue_lins, self.residue_norms)
         atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
         res, rmask = to_dense_batch(res, pg.get("batch"), **hints_p)
         atm, amask = to_dense_batch(atm, mg.get("batch"), **hints_m)
