@@ -25,6 +25,8 @@ struct WideDims {
 };
 
 // ---- register-tiled FFMA GEMM: C[M, N] = act(A[M, K] B[K, N] + bias), relu on columns < relu_cols -----------------------
+// 128 x 64 tile per CTA, 8 x 4 outputs per thread, K in steps of 16; the next K tile is fetched into registers
+// (float4 loads where lda / ldb / K allow) while the current one is multiplied out of shared memory.
 #define WG_BM 128
 #define WG_BN 64
 #define WG_BK 16
@@ -33,40 +35,60 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(long long M, int N, int 
                                                         float* __restrict__ C, int ldc, int relu_cols) {
     __shared__ __align__(16) float As[WG_BK][WG_BM + 4];
     __shared__ __align__(16) float Bs[WG_BK][WG_BN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads, 8 rows x 4 cols each
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads
     const long long m0 = (long long)blockIdx.x * WG_BM;
     const int n0 = blockIdx.y * WG_BN;
+    const bool a_vec = (lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool b_vec = (ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    // this thread's pieces of a K tile: A rows ar0, ar0 + 64 at k offset ak (4 values each); B row bk, 4 columns at bn
+    const int ar0 = tid >> 2, ak = (tid & 3) * 4;
+    const int bk = tid >> 4, bn = (tid & 15) * 4;
+    float4 ra[2], rb;
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const long long m = m0 + ar0 + 64 * q;
+            const int k = k0 + ak;
+            if (m < M && a_vec && k + 3 < K) ra[q] = __ldg(reinterpret_cast<const float4*>(A + m * lda + k));
+            else {
+                float t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = (m < M && k + j < K) ? __ldg(A + m * lda + k + j) : 0.f;
+                ra[q] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        const int k = k0 + bk, n = n0 + bn;
+        if (k < K && b_vec && n + 3 < N) rb = __ldg(reinterpret_cast<const float4*>(B + (long long)k * ldb + n));
+        else {
+            float t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = (k < K && n + j < N) ? __ldg(B + (long long)k * ldb + n + j) : 0.f;
+            rb = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int r = ar0 + 64 * q;
+            As[ak][r] = ra[q].x; As[ak + 1][r] = ra[q].y; As[ak + 2][r] = ra[q].z; As[ak + 3][r] = ra[q].w;
+        }
+        *reinterpret_cast<float4*>(&Bs[bk][bn]) = rb;
+    };
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    fetch(0);
     for (int k0 = 0; k0 < K; k0 += WG_BK) {
-        // A tile: 128 rows x 16 k, two (row, 4k) pieces per thread, stored k-major
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int piece = tid + q * 256, r = piece >> 2, kq = (piece & 3) * 4;
-            const long long m = m0 + r;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + kq + j;
-                As[kq + j][r] = (m < M && k < K) ? __ldg(A + m * lda + k) : 0.f;
-            }
-        }
-        {   // B tile: 16 k x 64 n, one float4 per thread
-            const int kr = tid >> 4, nc = (tid & 15) * 4;
-            const int k = k0 + kr;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + nc + j;
-                Bs[kr][nc + j] = (k < K && n < N) ? __ldg(B + (long long)k * ldb + n) : 0.f;
-            }
-        }
+        stash();
         __syncthreads();
+        if (k0 + WG_BK < K) fetch(k0 + WG_BK);               // in flight while this tile is multiplied
 #pragma unroll
         for (int k = 0; k < WG_BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            // rows ty*4 .. +3 and 64 + ty*4 .. +3: conflict-free float4 reads
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
             const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[4] = {b.x, b.y, b.z, b.w};
@@ -77,17 +99,23 @@ __global__ void __launch_bounds__(256) wide_gemm_kernel(long long M, int N, int 
         }
         __syncthreads();
     }
+    const bool c_vec = (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const long long m = m0 + ty * 8 + i;
+        const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (m >= M) continue;
+        const int n = n0 + tx * 4;
+        float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
-            if (n < relu_cols) v = fmaxf(v, 0.f);
-            C[m * ldc + n] = v;
+            v[j] = acc[i][j] + ((bias && n + j < N) ? __ldg(bias + n + j) : 0.f);
+            if (n + j < relu_cols) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (c_vec && n + 3 < N) *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < N) C[m * ldc + n + j] = v[j];
         }
     }
 }
