@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restr
 // Rows whose width is not a multiple of 16 bytes (the vector part: 3 * (2 nv + ev) floats): a CTA assembles
 // GV_EDGES message rows in shared memory (float4 loads of the node rows where they are 16-byte aligned, scalars for
 // the rest) and writes the assembled chunk -- contiguous in the output -- with coalesced float4 stores.
-#define GV_EDGES 64
+#define GV_EDGES 128
 __global__ void __launch_bounds__(256) gather_staged_kernel(const int64_t* __restrict__ ei, int64_t E, int w_node, int w_edge,
                                                             const float* __restrict__ node, const float* __restrict__ edge,
                                                             float* __restrict__ out, int node_vec4) {
