@@ -93,7 +93,7 @@ struct WarpSink {
 
     template <int KA, int NB, int NP, int AX, int BX>
     __device__ __forceinline__ void add(int off, const float (&A)[NP][AX], const float (&B)[NP][BX]) {
-        constexpr int KA4 = cdiv4(KA), NB4 = cdiv4(NB), NBP = NB4 * 4;
+        constexpr int KA4 = cdiv4(KA), NB4 = cdiv4(NB);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
 #pragma unroll
