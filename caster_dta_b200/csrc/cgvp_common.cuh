@@ -16,6 +16,7 @@
 #include "../../include/castergvp.h"
 
 #define CGVP_THREADS 128
+#define CGVP_MAX_THREADS 512   // generic conv kernels at wide dims: several threads per row
 #define CGVP_EPS 1e-8f
 #define CGVP_LN_EPS 1e-5f
 

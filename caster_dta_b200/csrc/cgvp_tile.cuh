@@ -345,6 +345,263 @@ __device__ __forceinline__ void gvp_bwd_row(const GvpP& g, const float* __restri
     }
 }
 
+// ---- team versions: T threads share one row ------------------------------------------------------------------------
+// At wide dims only a few rows fit in the shared-memory tile; a thread-per-row kernel would leave most of the CTA idle.
+// Here `tsz` threads (rank 0..tsz-1) work on the SAME row, each taking every tsz-th 8-column output block of a phase;
+// phases are separated by CTA barriers (every thread of the CTA must call these functions, `work` = this thread has a
+// row).  tsz = 1 reproduces the per-row functions above.
+template <class F>
+__device__ __forceinline__ void for_blocks_team(int n4, int rank, int tsz, F&& f) {
+    const int nb = (n4 + 1) >> 1;                       // blocks of 8 columns, the last one 4 if n4 is odd
+    for (int b = rank; b < nb; b += tsz) {
+        if (2 * b + 1 < n4) f(IC<8>{}, b * 8);
+        else f(IC<4>{}, b * 8);
+    }
+}
+
+template <bool SAVE>
+__device__ __forceinline__ void gvp_fwd_team(const GvpP& g, const float* __restrict__ W, float4* T, int rp, int r,
+                                             const StageIO& c, int rank, int tsz, bool work) {
+    if (work && g.vi > 0) {
+        const int hp = g.h4 * 4;
+        for_blocks_team(g.h4, rank, tsz, [&](auto obc, int o0) {
+            constexpr int OB = decltype(obc)::value;
+            float2 acc[3][OB / 2];
+            zero_acc(acc);
+            rl_block<OB, 3>(T + c.v_in * rp + r, c.v_in_pc * rp, rp, g.vi4, W + g.o_wh_t, hp, o0, acc);   // :152
+#pragma unroll
+            for (int j = 0; j < OB / 4; ++j)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    T[(c.vh + p * c.vh_pc + (o0 >> 2) + j) * rp + r] =
+                        make_float4(acc[p][2 * j].x, acc[p][2 * j].y, acc[p][2 * j + 1].x, acc[p][2 * j + 1].y);
+#pragma unroll
+            for (int i = 0; i < OB / 2; ++i) {                                                              // :153
+                const float qx = acc[0][i].x * acc[0][i].x + acc[1][i].x * acc[1][i].x + acc[2][i].x * acc[2][i].x;
+                const float qy = acc[0][i].y * acc[0][i].y + acc[1][i].y * acc[1][i].y + acc[2][i].y * acc[2][i].y;
+                const int o = o0 + 2 * i;
+                if (o < g.h) tile_at(T, rp, r, c.s_in, g.si + o) = sqrtf(fmaxf(qx, CGVP_EPS));
+                if (o + 1 < g.h) tile_at(T, rp, r, c.s_in, g.si + o + 1) = sqrtf(fmaxf(qy, CGVP_EPS));
+            }
+        });
+    }
+    if (work && rank == 0) {   // constant-1 column (bias row of ws_t) and zero padding up to the float4 boundary
+        int k = g.si + g.h;
+        tile_at(T, rp, r, c.s_in, k) = 1.f;
+        for (++k; k < g.ks4 * 4; ++k) tile_at(T, rp, r, c.s_in, k) = 0.f;
+    }
+    __syncthreads();
+    if (work) {
+        const int sop = g.so4 * 4;
+        for_blocks_team(g.so4, rank, tsz, [&](auto obc, int o0) {                                           // :154
+            constexpr int OB = decltype(obc)::value;
+            float2 acc[1][OB / 2];
+            zero_acc(acc);
+            rl_block<OB, 1>(T + c.s_in * rp + r, 0, rp, g.ks4, W + g.o_ws_t, sop, o0, acc);
+#pragma unroll
+            for (int j = 0; j < OB / 4; ++j) {
+                const float4 pre = make_float4(acc[0][2 * j].x, acc[0][2 * j].y, acc[0][2 * j + 1].x, acc[0][2 * j + 1].y);
+                T[(c.s_out + (o0 >> 2) + j) * rp + r] = act_fwd4(g.sact, pre);                             // :172-173
+                if (g.gate) T[(c.sp + (o0 >> 2) + j) * rp + r] = act_fwd4(g.vact, pre);                    // :159-162
+            }
+        });
+    }
+    __syncthreads();
+    if (g.vo > 0 && g.vi > 0 && g.gate) {
+        if (work && rank == 0) {
+            tile_at(T, rp, r, c.sp, g.so) = 1.f;
+            for (int k = g.so + 1; k < g.ksv4 * 4; ++k) tile_at(T, rp, r, c.sp, k) = 0.f;
+        }
+        __syncthreads();
+    }
+    if (work && g.vo > 0) {
+        if (g.vi > 0) {
+            const int vop = g.vo4 * 4;
+            for_blocks_team(g.vo4, rank, tsz, [&](auto obc, int o0) {
+                constexpr int OB = decltype(obc)::value;
+                float2 av[3][OB / 2];
+                zero_acc(av);
+                rl_block<OB, 3>(T + c.vh * rp + r, c.vh_pc * rp, rp, g.h4, W + g.o_wv_t, vop, o0, av);     // :156
+                float2 sg[1][OB / 2];
+                if (g.gate) {                                                                              // :158-163
+                    zero_acc(sg);
+                    rl_block<OB, 1>(T + c.sp * rp + r, 0, rp, g.ksv4, W + g.o_wsv_t, vop, o0, sg);
+#pragma unroll
+                    for (int i = 0; i < OB / 2; ++i) sg[0][i] = make_float2(sigmoidf_(sg[0][i].x), sigmoidf_(sg[0][i].y));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < OB / 2; ++i) {
+                        if (g.vact) {                                                                      // :164-166
+                            const float qx = av[0][i].x * av[0][i].x + av[1][i].x * av[1][i].x + av[2][i].x * av[2][i].x;
+                            const float qy = av[0][i].y * av[0][i].y + av[1][i].y * av[1][i].y + av[2][i].y * av[2][i].y;
+                            sg[0][i] = make_float2(act_fwd(g.vact, sqrtf(fmaxf(qx, CGVP_EPS))),
+                                                   act_fwd(g.vact, sqrtf(fmaxf(qy, CGVP_EPS))));
+                        } else {
+                            sg[0][i] = make_float2(1.f, 1.f);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < OB / 4; ++j) {
+                    const float4 s4 = make_float4(sg[0][2 * j].x, sg[0][2 * j].y, sg[0][2 * j + 1].x, sg[0][2 * j + 1].y);
+                    if (SAVE) T[(c.sg + (o0 >> 2) + j) * rp + r] = s4;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const float4 a4 = make_float4(av[p][2 * j].x, av[p][2 * j].y, av[p][2 * j + 1].x, av[p][2 * j + 1].y);
+                        if (SAVE) T[(c.vo + p * g.vo4 + (o0 >> 2) + j) * rp + r] = a4;
+                        T[(c.v_out + p * c.v_out_pc + (o0 >> 2) + j) * rp + r] =
+                            make_float4(a4.x * s4.x, a4.y * s4.y, a4.z * s4.z, a4.w * s4.w);
+                    }
+                }
+            });
+        } else {                                                                                           // :169-171
+            for (int j = rank; j < 3 * g.vo4; j += tsz) T[(c.v_out + j) * rp + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void gvp_bwd_team(const GvpP& g, const float* __restrict__ W, float4* T, int rp, int r,
+                                             const StageIO& c, const GradIO& d, int rank, int tsz, bool work) {
+    const bool has_v = g.vi > 0 && g.vo > 0;
+    if (work && has_v) {
+        for (int o4 = rank; o4 < g.vo4; o4 += tsz) {
+            float4 dv[3], vo[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                dv[p] = T[(d.gv_in + p * d.gv_in_pc + o4) * rp + r];
+                vo[p] = T[(c.vo + p * g.vo4 + o4) * rp + r];
+            }
+            const float4 sg = T[(c.sg + o4) * rp + r];
+            float4 dgv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float s = f4get(sg, i);
+                const float dx = f4get(dv[0], i), dy = f4get(dv[1], i), dz = f4get(dv[2], i);
+                const float vx = f4get(vo[0], i), vy = f4get(vo[1], i), vz = f4get(vo[2], i);
+                const float dot = dx * vx + dy * vy + dz * vz;
+                float ox, oy, oz, gg = 0.f;
+                if (g.gate) {
+                    gg = dot * s * (1.f - s);
+                    ox = dx * s; oy = dy * s; oz = dz * s;
+                } else if (g.vact) {
+                    const float q = vx * vx + vy * vy + vz * vz;
+                    const float t = q >= CGVP_EPS ? dot * act_bwd(g.vact, s) / sqrtf(q) : 0.f;
+                    ox = dx * s + vx * t; oy = dy * s + vy * t; oz = dz * s + vz * t;
+                } else {
+                    ox = dx; oy = dy; oz = dz;
+                }
+                reinterpret_cast<float*>(&dv[0])[i] = ox;
+                reinterpret_cast<float*>(&dv[1])[i] = oy;
+                reinterpret_cast<float*>(&dv[2])[i] = oz;
+                reinterpret_cast<float*>(&dgv)[i] = gg;
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p) T[(d.gv_in + p * d.gv_in_pc + o4) * rp + r] = dv[p];
+            if (g.gate) T[(d.dg + o4) * rp + r] = dgv;
+        }
+    }
+    __syncthreads();
+    if (work) {   // ds' = dS_out * sact'(s_out) + (dg . wsv) * vact'(gate_in)
+        if (g.gate) {
+            const int sop = g.so4 * 4;
+            for_blocks_team(g.so4, rank, tsz, [&](auto obc, int o0) {
+                constexpr int OB = decltype(obc)::value;
+                float2 acc[1][OB / 2];
+                zero_acc(acc);
+                rl_block<OB, 1>(T + d.dg * rp + r, 0, rp, g.vo4, W + g.o_wsv_b, sop, o0, acc);
+#pragma unroll
+                for (int j = 0; j < OB / 4; ++j) {
+                    const int col = (o0 >> 2) + j;
+                    const float4 ds = T[(d.gs_in + col) * rp + r];
+                    const float4 so = T[(c.s_out + col) * rp + r];
+                    const float4 gi = T[(c.sp + col) * rp + r];
+                    const float a[4] = {acc[0][2 * j].x, acc[0][2 * j].y, acc[0][2 * j + 1].x, acc[0][2 * j + 1].y};
+                    float4 o;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float*>(&o)[i] =
+                            f4get(ds, i) * act_bwd(g.sact, f4get(so, i)) + a[i] * act_bwd(g.vact, f4get(gi, i));
+                    T[(d.gs_in + col) * rp + r] = o;
+                }
+            });
+        } else if (g.sact) {
+            for (int col = rank; col < g.so4; col += tsz) {
+                float4 ds = T[(d.gs_in + col) * rp + r];
+                const float4 so = T[(c.s_out + col) * rp + r];
+                ds.x *= act_bwd(g.sact, so.x); ds.y *= act_bwd(g.sact, so.y);
+                ds.z *= act_bwd(g.sact, so.z); ds.w *= act_bwd(g.sact, so.w);
+                T[(d.gs_in + col) * rp + r] = ds;
+            }
+        }
+    }
+    __syncthreads();
+    if (work) {   // [dS_in ; dvn] = ds' . ws
+        const int np_ = g.ksd4 * 4;
+        for_blocks_team(g.ksd4, rank, tsz, [&](auto obc, int o0) {
+            constexpr int OB = decltype(obc)::value;
+            float2 acc[1][OB / 2];
+            zero_acc(acc);
+            rl_block<OB, 1>(T + d.gs_in * rp + r, 0, rp, g.so4, W + g.o_ws_b, np_, o0, acc);
+#pragma unroll
+            for (int j = 0; j < OB / 4; ++j)
+                T[(d.gs_out + (o0 >> 2) + j) * rp + r] =
+                    make_float4(acc[0][2 * j].x, acc[0][2 * j].y, acc[0][2 * j + 1].x, acc[0][2 * j + 1].y);
+        });
+    }
+    __syncthreads();
+    if (g.vi > 0) {
+        if (work) {   // dVh = wv^T dVo + Vh * dvn / vn   (clamp passes the gradient where |Vh|^2 >= eps)
+            const int hp = g.h4 * 4;
+            for_blocks_team(g.h4, rank, tsz, [&](auto obc, int o0) {
+                constexpr int OB = decltype(obc)::value;
+                float2 acc[3][OB / 2];
+                zero_acc(acc);
+                if (g.vo > 0) rl_block<OB, 3>(T + d.gv_in * rp + r, d.gv_in_pc * rp, rp, g.vo4, W + g.o_wv_b, hp, o0, acc);
+#pragma unroll
+                for (int j = 0; j < OB / 4; ++j) {
+                    const int col = (o0 >> 2) + j;
+                    float4 vh[3], o[3];
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) vh[p] = T[(c.vh + p * c.vh_pc + col) * rp + r];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = o0 + 4 * j + i;
+                        const float x = f4get(vh[0], i), y = f4get(vh[1], i), z = f4get(vh[2], i);
+                        const float q = x * x + y * y + z * z;
+                        float f = 0.f;
+                        if (k < g.h && q >= CGVP_EPS)
+                            f = tile_at(T, rp, r, d.gs_out, g.si + k) / tile_at(T, rp, r, c.s_in, g.si + k);
+                        const float2 a0 = acc[0][2 * j + (i >> 1)], a1 = acc[1][2 * j + (i >> 1)], a2 = acc[2][2 * j + (i >> 1)];
+                        reinterpret_cast<float*>(&o[0])[i] = ((i & 1) ? a0.y : a0.x) + x * f;
+                        reinterpret_cast<float*>(&o[1])[i] = ((i & 1) ? a1.y : a1.x) + y * f;
+                        reinterpret_cast<float*>(&o[2])[i] = ((i & 1) ? a2.y : a2.x) + z * f;
+                    }
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) T[(d.dvh + p * d.dvh_pc + col) * rp + r] = o[p];
+                }
+            });
+        }
+        __syncthreads();
+        if (work) {   // dV_in = wh^T dVh
+            const int vip = g.vi4 * 4;
+            for_blocks_team(g.vi4, rank, tsz, [&](auto obc, int o0) {
+                constexpr int OB = decltype(obc)::value;
+                float2 acc[3][OB / 2];
+                zero_acc(acc);
+                rl_block<OB, 3>(T + d.dvh * rp + r, d.dvh_pc * rp, rp, g.h4, W + g.o_wh_b, vip, o0, acc);
+#pragma unroll
+                for (int j = 0; j < OB / 4; ++j)
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+                        T[(d.gv_out + p * d.gv_out_pc + (o0 >> 2) + j) * rp + r] =
+                            make_float4(acc[p][2 * j].x, acc[p][2 * j].y, acc[p][2 * j + 1].x, acc[p][2 * j + 1].y);
+            });
+        }
+        __syncthreads();
+    }
+}
+
 // ---- LayerNorm for one row (gvp_layers.py:231-242) ------------------------------------------------------------
 // src -> dst (may alias).  Writes (mean, rstd, vector rms) to `stat` when stat >= 0.
 __device__ __forceinline__ void ln_fwd_row(float4* T, int rp, int r, int ns, int nv, int s_src, int v_src, int vpc,

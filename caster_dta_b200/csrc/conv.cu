@@ -32,6 +32,7 @@ struct ConvK {
     int goff[CGVP_MAX_CHAIN], partial_floats;
     // geometry
     int R, rp, ncols, w_smem, woff[CGVP_MAX_CHAIN], wtotal;
+    int team, threads;                    // threads per row (power of two) and per CTA (R * team <= threads)
     const float* wp[CGVP_MAX_CHAIN];
     long long E, N;
     int ntiles;
@@ -218,7 +219,7 @@ __device__ __forceinline__ ConvSmem carve(const ConvK& K, unsigned char* smem) {
 }
 
 template <bool WS>
-__global__ void __launch_bounds__(CGVP_THREADS) conv_fwd_kernel(const __grid_constant__ ConvK K) {
+__global__ void __launch_bounds__(CGVP_MAX_THREADS) conv_fwd_kernel(const __grid_constant__ ConvK K) {
     extern __shared__ __align__(16) unsigned char smem[];
     const ConvSmem sm = carve(K, smem);
     float4* T = sm.T;
@@ -237,9 +238,12 @@ __global__ void __launch_bounds__(CGVP_THREADS) conv_fwd_kernel(const __grid_con
         __syncthreads();
         stage_message_input(K, T, sm.ix, rv);
         __syncthreads();
-        if (threadIdx.x < rv)
+        {   // K.team threads per row; rows >= rv hold stale (finite) data and are never stored
+            const int row = threadIdx.x / K.team, rank = threadIdx.x % K.team;
             for (int k = 0; k < L; ++k)
-                gvp_fwd_row<false>(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, threadIdx.x, stage_io(K.cc, k));
+                gvp_fwd_team<false>(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, row < K.R ? row : 0, stage_io(K.cc, k), rank,
+                                    K.team, row < K.R);
+        }
         __syncthreads();
         segmented_reduce_tile(K, T, sm.ix, m, t, p0, rv, true, sm.flags);
         __syncthreads();
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(CGVP_THREADS) conv_fwd_kernel(const __grid_con
 }
 
 template <int NSLOT, bool WS>
-__global__ void __launch_bounds__(CGVP_THREADS) conv_bwd_kernel(const __grid_constant__ ConvK K) {
+__global__ void __launch_bounds__(CGVP_MAX_THREADS) conv_bwd_kernel(const __grid_constant__ ConvK K) {
     extern __shared__ __align__(16) unsigned char smem[];
     const ConvSmem sm = carve(K, smem);
     float4* T = sm.T;
@@ -279,15 +283,18 @@ __global__ void __launch_bounds__(CGVP_THREADS) conv_bwd_kernel(const __grid_con
                  K.aggr == CGVP_AGGR_MEAN ? sm.ix.scale : nullptr);
         zero_v_pad(T, rp, rv, K.gv[L], K.cc.vpc[L], K.vo);
         __syncthreads();
-        if (threadIdx.x < rv) {
-            const int r = threadIdx.x;
-            for (int k = 0; k < L; ++k) gvp_fwd_row<true>(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, r, stage_io(K.cc, k));
+        {
+            const int row = threadIdx.x / K.team, rank = threadIdx.x % K.team;
+            const bool work = row < K.R;
+            const int r = work ? row : 0;
+            for (int k = 0; k < L; ++k)
+                gvp_fwd_team<true>(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, r, stage_io(K.cc, k), rank, K.team, work);
             for (int k = L - 1; k >= 0; --k) {
                 GradIO d;
                 d.gs_in = K.gs[k + 1]; d.gv_in = K.gv[k + 1]; d.gv_in_pc = K.cc.vpc[k + 1];
                 d.gs_out = K.gs[k]; d.gv_out = K.gv[k]; d.gv_out_pc = K.cc.vpc[k];
                 d.dg = K.dg[k]; d.dvh = K.dvh[k]; d.dvh_pc = K.cc.vhpc[k];
-                gvp_bwd_row(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, r, stage_io(K.cc, k), d);
+                gvp_bwd_team(K.g[k], conv_weights<WS>(K, sm.wsm, k), T, rp, r, stage_io(K.cc, k), d, rank, K.team, work);
             }
         }
         __syncthreads();
@@ -392,6 +399,12 @@ static int conv_geometry(ConvK& K, int smem_max, bool backward, size_t* smem_byt
         }
         if (best_r > 0) {
             K.R = best_r; K.rp = best_r + 1; K.w_smem = pass == 0;
+            // few rows fit at wide dims: up to 8 threads team up on each row (more warps to hide latency, see gvp_fwd_team)
+            K.team = 1;
+            if ((best_r & (best_r - 1)) == 0 && best_r <= 64)
+                while (K.team < 8 && best_r * K.team * 2 <= CGVP_MAX_THREADS) K.team *= 2;
+            K.threads = best_r * K.team < CGVP_THREADS ? CGVP_THREADS : best_r * K.team;
+            if (K.team == 1) K.threads = CGVP_THREADS;
             K.wtotal = pass == 0 ? wt_full : 0;
             *smem_bytes = need(best_r);
             *ctas_per_sm = best_c;
@@ -493,10 +506,10 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
     cgvp_prof_begin(CGVP_K_CONV_FWD, st);
     if (K.w_smem) {
         CGVP_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<true><<<grid, CGVP_THREADS, smem, st>>>(K);
+        conv_fwd_kernel<true><<<grid, K.threads, smem, st>>>(K);
     } else {
         CGVP_CUDA(cudaFuncSetAttribute(conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<false><<<grid, CGVP_THREADS, smem, st>>>(K);
+        conv_fwd_kernel<false><<<grid, K.threads, smem, st>>>(K);
     }
     cgvp_prof_end(CGVP_K_CONV_FWD, st);
     CGVP_LAUNCH_CHECK("conv_fwd_kernel");
@@ -575,10 +588,10 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
         cgvp_prof_begin(CGVP_K_CONV_BWD, st);
         if (K.w_smem) {
             CGVP_CUDA(cudaFuncSetAttribute(conv_bwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conv_bwd_kernel<2, true><<<grid, CGVP_THREADS, smem, st>>>(K);
+            conv_bwd_kernel<2, true><<<grid, K.threads, smem, st>>>(K);
         } else {
             CGVP_CUDA(cudaFuncSetAttribute(conv_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conv_bwd_kernel<2, false><<<grid, CGVP_THREADS, smem, st>>>(K);
+            conv_bwd_kernel<2, false><<<grid, K.threads, smem, st>>>(K);
         }
         cgvp_prof_end(CGVP_K_CONV_BWD, st);
         CGVP_LAUNCH_CHECK("conv_bwd_kernel");
