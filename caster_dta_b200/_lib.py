@@ -66,6 +66,7 @@ SIGNATURES = {
     "cgvp_sm_count": (C.c_int32, []),
     "cgvp_set_fast_paths": (C.c_int32, [C.c_int32]),
     "cgvp_set_tensor_cores": (C.c_int32, [C.c_int32]),
+    "cgvp_set_wide_gemm": (C.c_int32, [C.c_int32]),
     "cgvp_profile_enable": (C.c_int32, [C.c_int32]),
     "cgvp_profile_collect": (C.c_int32, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cgvp_gvp_packed_floats": (C.c_int64, [C.POINTER(GvpDesc)]),

@@ -285,6 +285,12 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) wide_k3_kernel(const WideArgs
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 bool cgvp_fast_paths_enabled();
+int64_t gemm_tc_packed_floats(int N, int K);
+int gemm_tc_pack(const float* w, long long sn, long long sk, int N, int K, float* whi, float* wlo, cudaStream_t st);
+int gemm_tc(long long M, int N, int K, const float* A, long long lda, const float* whi, const float* wlo, const float* bias,
+            float* C, long long ldc, int relu_cols, cudaStream_t st);
+static bool g_wide_tensor_gemm = true;      // fp32-accurate 3xTF32 tcgen05 GEMM (gemm_tc.cu) instead of the FFMA GEMM
+extern "C" int32_t cgvp_set_wide_gemm(int32_t tensor) { g_wide_tensor_gemm = tensor != 0; return 0; }
 
 static bool wide_matches(const CgvpRowDesc* d, WideDims& w) {
     if (!(d->has_residual_in && d->pre_norm && d->post_residual && d->post_norm && d->n_gvp == 2 && d->onehot == 0)) return false;
@@ -309,6 +315,7 @@ static int64_t wide_layout(const WideDims& w, int64_t N, int64_t* off /*[12]*/) 
     off[6] = take(N * w.ka0); off[7] = take(N * 3 * w.h0);              // a0, vh0
     off[8] = take(N * w.n0); off[9] = take(N * 3 * w.h1);               // sg0 / a1, vh1
     off[10] = take(N * w.n1);                                           // sg1
+    off[11] = take(2 * (gemm_tc_packed_floats(w.n0, w.ka0) + gemm_tc_packed_floats(w.n1, w.ka1)));   // split weights (hi, lo) x 2 GEMMs
     return o + 256;
 }
 
@@ -352,13 +359,23 @@ int rows_fwd_wide(const CgvpRowDesc* desc, const CgvpRowArgs* args, void* ws, in
     if (fail("wide_pack_kernel")) return 1;
     const int grid = (int)(cdiv64(N, WIDE_WARPS) < (int64_t)sms * 8 ? cdiv64(N, WIDE_WARPS) : (int64_t)sms * 8);
     const int sc1 = w.ns + 3 * w.nv, sc2 = 3 * w.h0 + 3 * w.hv, sc3 = w.ns + 3 * w.nv + 3 * w.h1;
+    const bool tensor = g_wide_tensor_gemm && (w.ka0 & 3) == 0 && (w.n0 & 3) == 0;
+    float *whi0 = F(11), *wlo0 = whi0 + gemm_tc_packed_floats(w.n0, w.ka0), *whi1 = wlo0 + gemm_tc_packed_floats(w.n0, w.ka0),
+          *wlo1 = whi1 + gemm_tc_packed_floats(w.n1, w.ka1);
+    if (tensor) {                                          // Wf is [K][N]: W(n, k) = Wf[k * N + n]
+        if ((*rc = gemm_tc_pack(F(0), 1, w.n0, w.n0, w.ka0, whi0, wlo0, st))) return 1;
+        if ((*rc = gemm_tc_pack(F(2), 1, w.n1, w.n1, w.ka1, whi1, wlo1, st))) return 1;
+    }
+    const int relu0 = w.sact0 == CGVP_ACT_RELU ? w.hs : 0;
     cgvp_prof_begin(CGVP_K_ROWS_FWD, st);
     wide_k1_kernel<<<grid, WIDE_WARPS * 32, (size_t)WIDE_WARPS * sc1 * 4, st>>>(a, sc1);
-    wide_gemm_kernel<<<dim3((unsigned)cdiv64(N, WG_BM), (unsigned)cdiv(w.n0, WG_BN)), 256, 0, st>>>(
-        N, w.n0, w.ka0, a.a0, w.ka0, F(0), w.n0, F(1), a.sg0, w.n0, w.sact0 == CGVP_ACT_RELU ? w.hs : 0);
+    if (tensor) { if ((*rc = gemm_tc(N, w.n0, w.ka0, a.a0, w.ka0, whi0, wlo0, F(1), a.sg0, w.n0, relu0, st))) return 1; }
+    else wide_gemm_kernel<<<dim3((unsigned)cdiv64(N, WG_BM), (unsigned)cdiv(w.n0, WG_BN)), 256, 0, st>>>(
+            N, w.n0, w.ka0, a.a0, w.ka0, F(0), w.n0, F(1), a.sg0, w.n0, relu0);
     wide_k2_kernel<<<grid, WIDE_WARPS * 32, (size_t)WIDE_WARPS * sc2 * 4, st>>>(a, sc2);
-    wide_gemm_kernel<<<dim3((unsigned)cdiv64(N, WG_BM), (unsigned)cdiv(w.n1, WG_BN)), 256, 0, st>>>(
-        N, w.n1, w.ka1, a.sg0, w.n0, F(2), w.n1, F(3), a.sg1, w.n1, 0);
+    if (tensor) { if ((*rc = gemm_tc(N, w.n1, w.ka1, a.sg0, w.n0, whi1, wlo1, F(3), a.sg1, w.n1, 0, st))) return 1; }
+    else wide_gemm_kernel<<<dim3((unsigned)cdiv64(N, WG_BM), (unsigned)cdiv(w.n1, WG_BN)), 256, 0, st>>>(
+            N, w.n1, w.ka1, a.sg0, w.n0, F(2), w.n1, F(3), a.sg1, w.n1, 0);
     wide_k3_kernel<<<grid, WIDE_WARPS * 32, (size_t)WIDE_WARPS * sc3 * 4, st>>>(a, sc3);
     cgvp_prof_end(CGVP_K_ROWS_FWD, st);
     fail("wide node-update kernels");

@@ -68,6 +68,10 @@ int32_t cgvp_set_fast_paths(int32_t on);
  * W_h / W_s / W_mu / gate projections of the message GVPs run as tcgen05.mma with bf16 operands and fp32
  * accumulation in TMEM (<= 1e-2 of the reference, the bound BASELINE.json states for tensor-core modes). */
 int32_t cgvp_set_tensor_cores(int32_t on);
+/* Dense GEMMs of the wide node update (csrc/rows_wide.cu).  1 (default): fp32-accurate split-precision ("3xTF32":
+ * hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) tcgen05 GEMM (csrc/gemm_tc.cu); 0: register-tiled FFMA GEMM.
+ * Both meet the fp32 parity bound (<= 1e-4 of the reference). */
+int32_t cgvp_set_wide_gemm(int32_t tensor);
 
 /* ---- kernel timing (measurement aid; no reference counterpart) ------------------------------------------------
  * When enabled, the library brackets the MAIN kernel of each operator with cudaEvents on the caller's stream.
