@@ -11,19 +11,33 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn, warmup=3):
-        """`fn()` runs one step on static input tensors and returns a tensor (e.g. the loss)."""
+    def __init__(self, fn, grads=None, warmup=3):
+        """`fn()` runs one step (forward + backward) on static input tensors and returns a tensor (e.g. the loss).
+        `grads` (a `parallel.GradSync`) makes the captured backward ASSIGN the parameter gradients: `.grad` is None while
+        capturing, the tensors autograd creates are this graph's outputs, and `select()` re-attaches them to the
+        parameters when several graphs (e.g. one per input buffer) share one model."""
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(warmup):
+                if grads is not None:
+                    grads.reset()
                 fn()
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        if grads is not None:
+            grads.reset()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn()
+        self.grads = grads
+        self.grad_tensors = None if grads is None else [p.grad for p in grads.params]
+
+    def select(self):
+        if self.grads is not None:
+            for p, g in zip(self.grads.params, self.grad_tensors):
+                p.grad = g
 
     def replay(self):
         self.graph.replay()

@@ -62,6 +62,34 @@ class FlatGradBucket:
         return self.flat
 
 
+class GradSync:
+    """Gradient handling without the per-parameter accumulate kernels.
+
+    `.grad` is reset to None before every backward, so autograd hands each parameter its freshly computed gradient
+    tensor instead of launching one `add_` per parameter into a pre-zeroed buffer (158 tiny kernels per step for
+    CASTER-DTA(2,2)).  With more than one rank the gradients are flattened into ONE buffer (a single `cat`), all-reduced
+    once over NCCL / NVLink (3.06 MB) and copied back with one multi-tensor copy.  Works under CUDA-graph capture: the
+    gradient tensors created while capturing are the graph's own allocations and are rewritten in place on replay."""
+
+    def __init__(self, module, process_group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad and p.numel() > 0]
+        self.group = process_group
+        self.numel = sum(p.numel() for p in self.params)
+
+    def reset(self):
+        for p in self.params:
+            p.grad = None
+
+    def all_reduce_mean(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        grads = [p.grad for p in self.params]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(dist.get_world_size(self.group))
+        torch._foreach_copy_([g.view(-1) for g in grads], list(flat.split([g.numel() for g in grads])))
+
+
 def broadcast_parameters(module, src=0, process_group=None):
     """Replicas start from rank `src`'s weights."""
     if not (dist.is_available() and dist.is_initialized()):

@@ -16,6 +16,38 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _worker_sync(rank, world, port, ret):
+    """Same check for parallel.GradSync (gradients assigned by autograd, one cat + all-reduce + multi-tensor copy)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(123 + rank)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    parallel.broadcast_parameters(model, 0)
+    sync = parallel.GradSync(model)
+    data = torch.randn(8, 6, generator=torch.Generator().manual_seed(7))
+    for _ in range(2):                                  # twice: reset() must drop the previous step's gradients
+        sync.reset()
+        model(data[parallel.shard_pairs(8, rank, world)]).square().mean().backward()
+        sync.all_reduce_mean()
+    flat = torch.cat([p.grad.flatten() for p in sync.params])
+    ref_model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    ref_model.load_state_dict(model.state_dict())
+    total = sum(ref_model(data[parallel.shard_pairs(8, r, world)]).square().mean() for r in range(world)) / world
+    total.backward()
+    ref = torch.cat([p.grad.flatten() for p in ref_model.parameters()])
+    ret[rank] = (float((flat - ref).abs().max()), flat.tolist())
+    dist.destroy_process_group()
+
+
+def test_grad_sync_allreduce_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_sync, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] < 1e-6 and ret[1][0] < 1e-6
+    assert ret[0][1] == ret[1][1], "replicas must hold bit-identical reduced gradients"
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
