@@ -175,8 +175,32 @@ def conv_bytes_per_edge(kind, kbar, ns=16, nv=4, es=32, ev=1):
     return 2 * q + i + 3 * r / kbar               # + write d(edge row); read x, d_out and write d_x once per node
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (e.g. "NCCL version ..." from the first collective) must not share stdout with the ONE JSON line:
+    route fd 1 to stderr for the whole run and keep the real stdout for `emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,7 +214,7 @@ def main():
         sec, n, e = cpu_reference_steps(pb, mol, y, graph, args.steps, max(args.warmup, 1), threads)
         val = args.pairs / sec
         sample = f"{args.steps} full steps (fwd+bwd+Adam) on one {args.pairs}-pair {args.shape}-shape batch, N={n}, E={e}"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -463,7 +487,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
