@@ -238,18 +238,23 @@ __global__ void __launch_bounds__(FEAT_THREADS) feat_fill_kernel(const FeatK K) 
             remaining -= before;
             prefix |= (unsigned long long)bin << shift;
             pmask |= 255ull << shift;
+            const int in_bin = hist[wib][bin];
             __syncwarp();
-            // early exit: exactly `remaining` keys share the prefix -> every one of them is taken, T is irrelevant below it
+            // every key that shares the prefix is taken: the lower digits cannot change the selection
+            if (in_bin == remaining) break;
         }
-        const double T = __longlong_as_double((long long)prefix);
-        int ties_left = remaining;             // how many entries equal to T are still to be taken
+        // keep keys whose masked bits are below the prefix, and the first `remaining` keys (column order) that match it.
+        // (fp64 bit patterns of non-negative doubles order like the doubles; after all 8 digits "match" means d == T, which
+        //  reproduces np.argsort(...)[:, :k] with ties in column order, :319)
+        int ties_left = remaining;
         for (int64_t j0 = lo; j0 < hi; j0 += 32) {
             const int64_t j = j0 + lane;
             double d = 0.0;
             bool lt = false, eq = false;
             if (j < hi && (K.keep_self || j != i)) {
-                d = cached ? __longlong_as_double((long long)drow[j - lo]) : ca_distance(K.ca, i, j);
-                lt = d < T; eq = d == T;
+                const unsigned long long key = cached ? drow[j - lo] : (unsigned long long)__double_as_longlong(ca_distance(K.ca, i, j));
+                d = __longlong_as_double((long long)key);
+                lt = (key & pmask) < prefix; eq = (key & pmask) == prefix;
             }
             const unsigned eqm = __ballot_sync(0xffffffffu, eq);
             const bool take_eq = eq && __popc(eqm & ((1u << lane) - 1u)) < ties_left;
