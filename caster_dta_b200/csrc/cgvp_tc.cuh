@@ -73,12 +73,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 // bf16-operand mode: approximate SFU maths is far inside the mode's error budget
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-// 8 consecutive K values of one row -> one 16-byte core-matrix row
+__device__ __forceinline__ float fast_sigmoid(float x) {                 // 0.5 tanh(x / 2) + 0.5, one MUFU
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+// 8 consecutive K values of one row -> one 16-byte core-matrix row; PITCH = bytes between k-chunks (the LBO)
+template <int PITCH>
 __device__ __forceinline__ void put8(unsigned char* region, int chunk, int row, const float (&v)[8]) {
     uint4 q;
     q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(region + chunk * 2048 + row * 16) = q;
+    *reinterpret_cast<uint4*>(region + chunk * PITCH + row * 16) = q;
 }
 }  // namespace tcx
 using namespace tcx;
