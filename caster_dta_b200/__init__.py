@@ -8,9 +8,10 @@ from .modules import (GVP, Dropout, GVPConv, GVPConvLayer, LayerNorm, _merge, _n
                       tuple_cat, tuple_index, tuple_sum)
 from .encoder import SelectableProteinModelWrapper, VectorProteinGNN_LBAModel
 from .joint import JointGNN, load_state_dict_from_checkpoint
-from .featurizer import residue_graph_batch
+from . import batching
+from .featurizer import residue_graph_batch, residue_node_features, aa_property_table, protein_graph_batch
 from .ops import GraphPlan, gather_message_input, get_plan, segment_reduce
 
 __all__ = ["GVP", "LayerNorm", "Dropout", "GVPConv", "GVPConvLayer", "tuple_sum", "tuple_cat", "tuple_index", "randn",
            "VectorProteinGNN_LBAModel", "SelectableProteinModelWrapper", "JointGNN", "load_state_dict_from_checkpoint",
-           "residue_graph_batch", "GraphPlan", "get_plan", "gather_message_input", "segment_reduce"]
+           "residue_graph_batch", "residue_node_features", "aa_property_table", "protein_graph_batch", "GraphPlan", "get_plan", "gather_message_input", "segment_reduce"]

@@ -97,6 +97,8 @@ SIGNATURES = {
     "cgvp_featurize_fill": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_node_features": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 KERNEL_IDS = {"conv_fwd": 0, "conv_bwd": 1, "rows_fwd": 2, "rows_bwd": 3, "segment_reduce": 4, "gather": 5,

@@ -354,3 +354,103 @@ extern "C" int32_t cgvp_featurize_fill(const float* ca, const int64_t* ptr, int6
     CGVP_LAUNCH_CHECK("feat_fill_kernel");
     return 0;
 }
+
+// ---- residue NODE features --------------------------------------------------------------------------------------------------
+// compute_residue_node_features(vectorize_features=True, add_esm2_embeds=False), utils/create_protein_features.py:12-198.
+// One thread per residue.  The reference works in numpy fp32 with separately rounded operations (no FMA contraction):
+// differences, np.linalg.norm = sqrt((x*x + y*y) + z*z), np.cross = a*b - c*d, divide; the side-chain combination is
+// evaluated in fp64 (np.sqrt(1/3) is a float64 scalar, :92) and cast to fp32 with the rest at create_graphs.py:21-23.
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3_sub(V3 a, V3 b) { return {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ V3 v3_add(V3 a, V3 b) { return {__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)}; }
+__device__ __forceinline__ float v3_dot(V3 a, V3 b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ V3 v3_cross(V3 a, V3 b) {
+    return {__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+            __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x))};
+}
+__device__ __forceinline__ V3 v3_unit(V3 a) {                          // normalize_vecs, :360-365 (0 where the norm is 0)
+    const float n = __fsqrt_rn(v3_dot(a, a));
+    if (n == 0.f) return {0.f, 0.f, 0.f};
+    return {__fdiv_rn(a.x, n), __fdiv_rn(a.y, n), __fdiv_rn(a.z, n)};
+}
+__device__ __forceinline__ V3 atom(const float* __restrict__ c, int64_t res, int a) {
+    const float* p = c + (res * 4 + a) * 3;
+    return {p[0], p[1], p[2]};
+}
+
+__global__ void node_feat_kernel(const float* __restrict__ coords, const int64_t* __restrict__ ptr, int64_t B, int64_t N,
+                                 const int64_t* __restrict__ idents, const float* __restrict__ table, int num_types, int num_props,
+                                 int posenc, float* __restrict__ out_s, float* __restrict__ out_v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t b = find_protein(ptr, B, i);
+    const int64_t lo = ptr[b], n = ptr[b + 1] - lo, li = i - lo;
+    const int width = 6 + num_props + (posenc ? 16 : 0);
+    float* s = out_s + i * width;
+    // dihedrals (:34-66): backbone atoms N, CA, C of all residues in one chain; unit bond vectors u[k] = atom[k+1] - atom[k];
+    // angle A[m] from (u[m], u[m+1], u[m+2]); residue li holds [0 ; A ; 0 ; 0][3 li .. 3 li + 2]
+    float ang[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int64_t e = 3 * li + t;
+        ang[t] = 0.f;
+        if (e >= 1 && e < 3 * n - 2) {
+            const int64_t m = e - 1;                                     // needs atoms m .. m + 3
+            V3 p[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p[q] = atom(coords, lo + (m + q) / 3, (int)((m + q) % 3));
+            const V3 u2 = v3_unit(v3_sub(p[1], p[0])), u1 = v3_unit(v3_sub(p[2], p[1])), u0 = v3_unit(v3_sub(p[3], p[2]));
+            const V3 n1 = v3_unit(v3_cross(u1, u0)), n2 = v3_unit(v3_cross(u2, u1));
+            const float c = fminf(fmaxf(v3_dot(n1, n2), -1.f), 1.f);
+            const float sg = v3_dot(n1, u2);
+            ang[t] = acosf(c) * (sg > 0.f ? 1.f : (sg < 0.f ? -1.f : 0.f));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { s[t] = cosf(ang[t]); s[3 + t] = sinf(ang[t]); }
+    // amino-acid property columns (:95-109): a table look-up
+    if (num_props > 0) {
+        const int64_t id = idents[i];
+        for (int j = 0; j < num_props; ++j) s[6 + j] = (id >= 0 && id < num_types) ? table[id * num_props + j] : 0.f;
+    }
+    // positional encoding of the residue index (:121-124, :368-385), fp64 like the reference
+    if (posenc) {
+        for (int k = 0; k < 8; ++k) {
+            const double f = exp(2.0 * (double)k * -(log(10000.0) / 8.0));
+            const double a = (double)li * f;
+            s[6 + num_props + k] = (float)cos(a);
+            s[6 + num_props + 8 + k] = (float)sin(a);
+        }
+    }
+    // orientations (:69-78) and the virtual side chain (:81-92)
+    const V3 ca = atom(coords, i, 1);
+    V3 f = {0.f, 0.f, 0.f}, bk = {0.f, 0.f, 0.f};
+    if (li + 1 < n) f = v3_unit(v3_sub(atom(coords, i + 1, 1), ca));
+    if (li > 0) { const V3 t = v3_unit(v3_sub(ca, atom(coords, i - 1, 1))); bk = {-t.x, -t.y, -t.z}; }
+    const V3 nv = v3_unit(v3_sub(atom(coords, i, 0), ca)), cv = v3_unit(v3_sub(atom(coords, i, 2), ca));
+    const V3 bis = v3_unit(v3_add(nv, cv)), perp = v3_unit(v3_cross(cv, nv));
+    const double k1 = sqrt(1.0 / 3.0), k2 = sqrt(2.0 / 3.0);
+    float* v = out_v + i * 9;
+    v[0] = f.x; v[1] = f.y; v[2] = f.z;
+    v[3] = bk.x; v[4] = bk.y; v[5] = bk.z;
+    v[6] = (float)__dsub_rn(__dmul_rn(-(double)bis.x, k1), __dmul_rn((double)perp.x, k2));
+    v[7] = (float)__dsub_rn(__dmul_rn(-(double)bis.y, k1), __dmul_rn((double)perp.y, k2));
+    v[8] = (float)__dsub_rn(__dmul_rn(-(double)bis.z, k1), __dmul_rn((double)perp.z, k2));
+}
+
+extern "C" int32_t cgvp_node_features(const float* res_coords, const int64_t* ptr, int64_t num_proteins, int64_t num_nodes,
+                                      const int64_t* idents, const float* aa_table, int32_t num_types, int32_t num_props,
+                                      int32_t add_posenc, float* out_s, float* out_v, void* stream) {
+    CGVP_REQUIRE(num_proteins >= 0 && num_nodes >= 0, "node_features: bad sizes");
+    CGVP_REQUIRE(num_props >= 0 && num_types >= 0, "node_features: bad table shape");
+    if (num_nodes == 0) return 0;
+    CGVP_REQUIRE(res_coords && ptr && out_s && out_v && num_proteins > 0, "node_features: null input");
+    CGVP_REQUIRE(num_props == 0 || (idents && aa_table && num_types > 0), "node_features: property table without identities");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    node_feat_kernel<<<(unsigned)cdiv64(num_nodes, 128), 128, 0, st>>>(res_coords, ptr, num_proteins, num_nodes, idents, aa_table,
+                                                                       num_types, num_props, add_posenc != 0, out_s, out_v);
+    CGVP_LAUNCH_CHECK("node_feat_kernel");
+    return 0;
+}

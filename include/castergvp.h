@@ -217,6 +217,18 @@ int32_t cgvp_featurize_fill(const float* ca, const int64_t* ptr, int64_t num_pro
                             const int64_t* row_offsets, int64_t* edge_index, int64_t num_edges, float* edge_s,
                             float* edge_v, void* ws, int64_t ws_bytes, cgvp_stream_t stream);
 
+/* ---- residue node features ------------------------------------------------------------------------------------
+ * Replaces compute_residue_node_features(vectorize_features=True, add_esm2_embeds=False)
+ * (utils/create_protein_features.py:12-198) for a batch of proteins:
+ *   res_coords:[N,4,3] fp32 backbone atoms (N, CA, C, O) of all proteins back to back, ptr:[B+1] int64.
+ *   out_s:[N, 6 + num_props + 16*add_posenc] = [cos(phi,psi,omega) ; sin(phi,psi,omega) ; aa_table[idents] ; pos-enc],
+ *   out_v:[N,3,3] = [forward ; backward ; virtual side chain] unit-vector features.
+ * aa_table:[num_types,num_props] fp32 is the caller's amino-acid property table (utils/protein_definitions.py:71-277,
+ * min-max normalised as the reference does); num_props = 0 skips the look-up (include_aa_props=False). */
+int32_t cgvp_node_features(const float* res_coords, const int64_t* ptr, int64_t num_proteins, int64_t num_nodes,
+                           const int64_t* idents, const float* aa_table, int32_t num_types, int32_t num_props,
+                           int32_t add_posenc, float* out_s, float* out_v, cgvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

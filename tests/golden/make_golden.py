@@ -17,6 +17,8 @@ Fixtures:
   lba_checkpoint.npz protein-GNN slice of the shipped checkpoint (15 117 parameters) + a small synthetic batch
                      (radius 4 A and kNN-10 graphs) + the reference embeddings [N,64].
   joint_small.npz    a reduced-width JointGNN (random init, seed 9): state_dict, batch, predicted affinity.
+  sampler.json       mini-batches produced by the reference PMD_BatchSampler (dataset/dual_dataset.py:424-522) on a
+                     seeded list of pair sizes, several settings, shuffle off.
 """
 import json
 import os
@@ -341,9 +343,53 @@ def make_joint_small():
     print("joint_small.npz", len(store), "arrays")
 
 
+def make_sampler():
+    """`dataset/dual_dataset.py` imports mdtraj / rdkit at module level, so the sampler class alone is compiled from
+    its own source text (located with `ast`, executed unchanged) and driven with a stand-in dataset."""
+    import ast
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "dataset", "dual_dataset.py")
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "PMD_BatchSampler")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    sampler_cls = ns["PMD_BatchSampler"]
+
+    class G:
+        def __init__(self, n, e):
+            self.num_nodes, self.num_edges = n, e
+
+    rng = np.random.default_rng(9)
+    pairs = 200
+    pn = rng.integers(25, 2000, size=pairs)
+    pe = pn * 30 - rng.integers(0, 200, size=pairs)
+    mn = rng.integers(8, 60, size=pairs)
+    me = mn * 3 + rng.integers(0, 6, size=pairs)
+    data = [(G(int(a), int(b)), G(int(c), int(d)), None) for a, b, c, d in zip(pn, pe, mn, me)]
+    settings = [
+        dict(max_num=400000, count_elem="edge", graph_type="both", include_nodepair=True, max_bsize=None),
+        dict(max_num=400000, count_elem="edge", graph_type="both", include_nodepair=True, max_bsize=8),
+        dict(max_num=150000, count_elem="edge", graph_type="protein", include_nodepair=False, max_bsize=None),
+        dict(max_num=6000, count_elem="node", graph_type="both", include_nodepair=False, max_bsize=32),
+        dict(max_num=900, count_elem="edge", graph_type="molecule", include_nodepair=False, max_bsize=None),
+        dict(max_num=30000, count_elem="node", graph_type="both", include_nodepair=True, max_bsize=None),
+    ]
+    cases = []
+    for kw in settings:
+        batches = [list(b) for b in sampler_cls(data, shuffle=False, skip_too_big=False, **kw)]
+        cases.append({"kwargs": kw, "batches": batches})
+    out = {"protein_nodes": pn.tolist(), "protein_edges": pe.tolist(), "molecule_nodes": mn.tolist(),
+           "molecule_edges": me.tolist(), "cases": cases}
+    json.dump(out, open(os.path.join(HERE, "sampler.json"), "w"))
+    print("sampler.json", [len(c["batches"]) for c in cases], "batches")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "sampler":
+        make_sampler()
+        sys.exit(0)
     make_gvp_units()
     make_featurizer()
     make_lba_checkpoint()
     make_joint_small()
+    make_sampler()

@@ -226,6 +226,83 @@ def test_featurizer_golden(setting):
     assert int(et.abs().sum()) == 0
 
 
+def _aa_table_from_golden(g):
+    """The reference's amino-acid property rows, recovered from its own output (identity -> columns 6..16)."""
+    tab = np.zeros((20, 11), np.float32)
+    for prot in ("p41", "p97"):
+        tab[g[f"{prot}/idents"]] = g[f"{prot}/node_s"][:, 6:]
+    return tab
+
+
+def test_node_features_golden():
+    """compute_residue_node_features of the reference (two proteins as ONE batch): look-up columns bit-exact,
+    geometry within fp32 libm noise (acos/cos/sin implementations differ by an ulp or two)."""
+    cg = _mods()
+    g = golden("featurizer")
+    coords = torch.from_numpy(np.concatenate([g["p41/coords"], g["p97/coords"]])).to(DEV)
+    idents = torch.from_numpy(np.concatenate([g["p41/idents"], g["p97/idents"]])).to(DEV)
+    ptr = torch.tensor([0, 41, 41 + 97])
+    s, v = cg.residue_node_features(coords, ptr, idents, torch.from_numpy(_aa_table_from_golden(g)))
+    ref_s = np.concatenate([g["p41/node_s"], g["p97/node_s"]])
+    ref_v = np.concatenate([g["p41/node_v"], g["p97/node_v"]])
+    assert s.shape == (138, 17) and v.shape == (138, 3, 3)
+    assert np.array_equal(s.cpu().numpy()[:, 6:], ref_s[:, 6:])
+    assert np.abs(s.cpu().numpy()[:, :6] - ref_s[:, :6]).max() <= 2e-6
+    assert np.abs(v.cpu().numpy() - ref_v).max() <= 1e-6
+    # forward / backward orientation rows are plain fp32 differences and divisions: bit-exact
+    assert np.array_equal(v.cpu().numpy()[:, :2], ref_v[:, :2])
+
+
+def test_node_features_batch_vs_oracle():
+    """Davis-shape batch incl. 1- and 2-residue chains, against the oracle per protein; positional-encoding columns
+    against the fp64 formula (`:368-385`)."""
+    cg = _mods()
+    from oracle import featurizer_oracle
+    from caster_dta_b200 import synth
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 3] + [int(x) for x in rng.integers(300, 1000, size=12)]
+    cs = [synth.random_backbone(n, rng) for n in lens]
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum(lens)]))
+    s, v = cg.residue_node_features(torch.from_numpy(np.concatenate(cs)).to(DEV), ptr, add_residue_posenc=True)
+    assert s.shape[1] == 22
+    s, v = s.cpu().numpy(), v.cpu().numpy()
+    o = 0
+    for n, c in zip(lens, cs):
+        rs, rv = featurizer_oracle.node_geometry_features(c)
+        assert np.abs(s[o:o + n, :6] - rs).max() <= 2e-6
+        assert np.abs(v[o:o + n] - rv).max() <= 1e-6
+        f = np.exp(2 * np.arange(8) * -(np.log(10000.0) / 8))
+        a = np.arange(n)[:, None] * f[None]
+        pe = np.concatenate([np.cos(a), np.sin(a)], -1).astype(np.float32)
+        assert np.abs(s[o:o + n, 6:] - pe).max() <= 1e-7
+        o += n
+
+
+def test_protein_graph_batch_feeds_the_encoder():
+    """coords -> features -> graph -> encoder entirely on the device equals the encoder on separately built inputs."""
+    cg = _mods()
+    from caster_dta_b200 import synth
+    rng = np.random.default_rng(11)
+    lens = [37, 120, 64]
+    coords = torch.from_numpy(np.concatenate([synth.random_backbone(n, rng) for n in lens])).to(DEV)
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum(lens)]))
+    idents = torch.from_numpy(rng.integers(0, 20, size=sum(lens)))
+    table = torch.from_numpy(rng.random((20, 11)).astype(np.float32))
+    d = cg.protein_graph_batch(coords, ptr, idents, table, 10, "num", True)
+    assert d["x"][0].shape == (221, 17) and d["x"][1].shape == (221, 3, 3)
+    assert d["batch"].cpu().tolist() == [0] * 37 + [1] * 120 + [2] * 64
+    ei, ea, et = cg.residue_graph_batch(coords, ptr, 10, "num", True)
+    assert torch.equal(d["edge_index"], ei) and torch.equal(d["eattr"][0], ea[0])
+    torch.manual_seed(0)
+    enc = cg.SelectableProteinModelWrapper(in_channels=(17, 3), edge_dim=(32, 1), base_conv="lbamodel", num_ntypes=20,
+                                           num_etypes=1, ntype_emb_dim=None, etype_emb_dim=None,
+                                           hidden_channels=(16, 4), edge_hidden_channels=(32, 1), out_channels=64,
+                                           num_convs=2).to(DEV).eval()
+    with torch.no_grad():
+        out = enc(**d)
+    assert out.shape == (221, 64) and bool(torch.isfinite(out).all())
+
+
 # ---- oracle comparisons at sizes the golden files do not cover ---------------------------------------------------------
 def _random_layer_case(n, e, nd, ed, seed, hub=False, aggr="sum"):
     from oracle import gvp_oracle
