@@ -198,7 +198,9 @@ CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::
 //     G[offset + a * pad4(NB) + b] += sum_p A[p][a] * B[p][b]          (layout of the forward packed block),
 // interleaved with the data path so that operands die as early as possible.
 // On entry gs / gv hold the gradient of the GVP outputs; on exit dsin = [dS_in ; dvn] and dvin = dV_in.
-template <class G, class Sink>
+// NEED_DX = false (the GVP reads leaf data, e.g. the raw edge / node features): only the weight gradients are wanted,
+// so dS_in and dV_in are not formed (dvn still is: it feeds dW_h).
+template <class G, class Sink, bool NEED_DX = true>
 CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, const float (&s)[1][G::SI],
                             const float (&v)[3][G::VI1], const float (&gs)[1][G::SO], const float (&gv)[3][G::VO1],
                             Sink& sink, int goff, float (&dsin)[1][G::KSD], float (&dvin)[3][G::VI1]) {
@@ -253,7 +255,12 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         sink.template add<G::KS, G::SO, 1>(goff + G::O_WS_T, a, ds);
     }
     zero2(dsin);
-    mv<G::SO, G::KSD, G::KSDP, 0, 0>(W + G::O_WS_B, ds, dsin);              // [dS_in ; dvn] = ds' . ws
+    if constexpr (NEED_DX || G::VI == 0) {
+        if constexpr (NEED_DX) mv<G::SO, G::KSD, G::KSDP, 0, 0>(W + G::O_WS_B, ds, dsin);   // [dS_in ; dvn] = ds' . ws
+    } else {
+        constexpr int C0 = G::SI / 4 * 4;                                   // dvn columns only (from a 16-byte boundary)
+        mv<G::SO, G::KSD - C0, G::KSDP, 0, C0>(W + G::O_WS_B + C0, ds, dsin);
+    }
     if constexpr (G::VI > 0) {
         float dvh[3][G::H1];
         zero2(dvh);
@@ -270,7 +277,7 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         }
         sink.template add<G::VI, G::H, 3>(goff + G::O_WH_T, v, dvh);
         zero2(dvin);
-        mv<G::H, G::VI, G::VIP, 0, 0>(W + G::O_WH_B, dvh, dvin);            // dV_in = wh^T dVh
+        if constexpr (NEED_DX) mv<G::H, G::VI, G::VIP, 0, 0>(W + G::O_WH_B, dvh, dvin);     // dV_in = wh^T dVh
     }
 }
 

@@ -319,7 +319,11 @@ __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __gri
             Save<G0> sv;
             float so[1][G0::SO], vo[3][G0::VO1], dsin[1][G0::KSD], dvin[3][G0::VI1];
             gvp_fwd<G0>(wsm, f.ys, f.yv, so, vo, sv);
-            gvp_bwd<G0>(wsm, sv, f.ys, f.yv, gs, gv, sink, S::GO0, dsin, dvin);
+            // an embed of leaf features (no residual, no pre-norm, nobody asks for d_in) needs weight gradients only
+            if (S::PRE_NORM || S::POST_RES || S::RES_IN || A.g.d_in_s || A.g.d_in_v)
+                gvp_bwd<G0>(wsm, sv, f.ys, f.yv, gs, gv, sink, S::GO0, dsin, dvin);
+            else
+                gvp_bwd<G0, decltype(sink), false>(wsm, sv, f.ys, f.yv, gs, gv, sink, S::GO0, dsin, dvin);
 #pragma unroll
             for (int c = 0; c < S::S0; ++c) dys[0][c] = dsin[0][c];
 #pragma unroll

@@ -119,6 +119,77 @@ def to_dense_batch(x, batch, num_graphs=None, max_nodes=None):
     return out, mask
 
 
+class DenseIndex:
+    """Row map between the packed layout [total, D] (graphs back to back) and the padded layout [B, max, D], computed
+    once per forward and shared by every pad / unpad.  The row-wise layers of the cross-attention block (LayerNorm,
+    projections, feed-forward, residuals) run on packed rows -- the padded layout of the reference
+    (`to_dense_batch`, `models/joint_gnn.py:197-204`) spends ~1/3 of its rows on padding at Davis-shape lengths -- and
+    only the attention core sees padded tensors.  No device->host sync when num_graphs / max_nodes are given."""
+
+    def __init__(self, batch, total, num_graphs=None, max_nodes=None, device=None):
+        if batch is None:
+            self.b, self.m = 1, int(total)
+            self.idx = torch.arange(total, device=device)
+            self.mask = torch.ones(1, total, dtype=torch.bool, device=device)
+            return
+        dev = batch.device
+        self.b = int(batch[-1]) + 1 if num_graphs is None else int(num_graphs)
+        counts = torch.zeros(self.b, dtype=torch.long, device=dev).index_add_(0, batch, torch.ones_like(batch))
+        start = torch.cumsum(counts, 0) - counts
+        self.m = int(counts.max()) if max_nodes is None else int(max_nodes)
+        self.idx = batch * self.m + (torch.arange(total, device=dev) - start[batch])
+        self.mask = torch.arange(self.m, device=dev).unsqueeze(0) < counts.unsqueeze(1)
+
+    def pad(self, x, fill=None):
+        """[total, D] -> [B, max, D]; padding rows hold `fill` ([D]) or zeros."""
+        d = x.shape[1]
+        out = x.new_zeros((self.b * self.m, d)) if fill is None else fill.to(x.dtype).expand(self.b * self.m, d).clone()
+        return out.index_copy(0, self.idx, x).view(self.b, self.m, d)
+
+    def unpad(self, dense):
+        return dense.reshape(self.b * self.m, dense.shape[-1]).index_select(0, self.idx)
+
+
+def _mha_packed(mha, q_in, kv_in, dq, dk, q_fill_in, return_weights, training):
+    """`nn.MultiheadAttention.forward(query, key, value, key_padding_mask=~mask)` (`models/joint_gnn.py:350-361`) with
+    the in / out projections on packed rows.  q_fill_in: the value every padded QUERY row has in the reference (the
+    LayerNorm bias -- LayerNorm of an all-zero row), so that the returned attention map matches on padded rows too."""
+    e, h = mha.embed_dim, mha.num_heads
+    hd = e // h
+    if mha._qkv_same_embed_dim:
+        wq, wkv = mha.in_proj_weight[:e], mha.in_proj_weight[e:]
+        wk = wv = None
+    else:
+        wq, wk, wv, wkv = mha.q_proj_weight, mha.k_proj_weight, mha.v_proj_weight, None
+    bq = bk = bv = bkv = None
+    if mha.in_proj_bias is not None:
+        bq, bkv = mha.in_proj_bias[:e], mha.in_proj_bias[e:]
+        bk, bv = mha.in_proj_bias[e:2 * e], mha.in_proj_bias[2 * e:]
+    q = F.linear(q_in, wq, bq)
+    if wkv is not None:
+        k, v = F.linear(kv_in, wkv, bkv).split(e, dim=-1)
+    else:
+        k, v = F.linear(kv_in, wk, bk), F.linear(kv_in, wv, bv)
+    q_fill = F.linear(q_fill_in, wq, bq) if q_fill_in is not None else None
+    qd = dq.pad(q, q_fill).view(dq.b, dq.m, h, hd).transpose(1, 2)                 # [B, H, Lq, hd]
+    kd = dk.pad(k).view(dk.b, dk.m, h, hd).transpose(1, 2)
+    vd = dk.pad(v).view(dk.b, dk.m, h, hd).transpose(1, 2)
+    key_mask = dk.mask[:, None, None, :]                                             # True = real key
+    p_drop = mha.dropout if training else 0.0
+    weights = None
+    if return_weights:
+        scores = torch.matmul(qd * (1.0 / hd) ** 0.5, kd.transpose(-2, -1)).masked_fill(~key_mask, float("-inf"))
+        prob = torch.softmax(scores, dim=-1)
+        if p_drop > 0.0:
+            prob = F.dropout(prob, p=p_drop)
+        od = torch.matmul(prob, vd)
+        weights = prob.mean(dim=1)                                                   # averaged over heads
+    else:
+        od = F.scaled_dot_product_attention(qd, kd, vd, attn_mask=key_mask, dropout_p=p_drop)
+    o = dq.unpad(od.transpose(1, 2).reshape(dq.b, dq.m, e))
+    return mha.out_proj(o), weights
+
+
 class CrossAttentionModule(nn.Module):
     def __init__(self, embed_dim_1, embed_dim_2, n_attention_heads, attn_dropout, include_residual_stream=True,
                  dim_feedforward_scale=2, feedforward_dropout=0.2):
@@ -150,6 +221,22 @@ class CrossAttentionModule(nn.Module):
             e1, e2 = a1, a2
         return e1, e2, (w1, w2)
 
+    def forward_packed(self, x1, x2, d1, d2, return_weights=True, first=True):
+        """Same block (`models/joint_gnn.py:321-408`) on packed rows x1 [N1, D1], x2 [N2, D2]; d1 / d2: DenseIndex."""
+        n1, n2 = self.preattn_norm1(x1), self.preattn_norm2(x2)
+        f1 = self.preattn_norm1.bias if first else None
+        f2 = self.preattn_norm2.bias if first else None
+        a1, w1 = _mha_packed(self.embed1_to_2, n1, n2, d1, d2, f1, return_weights, self.training)
+        a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
+        if self.include_residual_stream:
+            x1 = x1 + self.ff_dropout(a1)
+            x1 = x1 + self.ff_dropout(self.ff1(self.ff_norm1(x1)))
+            x2 = x2 + self.ff_dropout(a2)
+            x2 = x2 + self.ff_dropout(self.ff2(self.ff_norm2(x2)))
+        else:
+            x1, x2 = a1, a2
+        return x1, x2, (w1, w2)
+
 
 class StackedCrossAttentionModule(nn.Module):
     def __init__(self, make_layer, num_layers):
@@ -162,6 +249,15 @@ class StackedCrossAttentionModule(nn.Module):
             e1, e2, w = layer(e1, e2, mask1, mask2, return_weights)
             weights.append(w)
         return e1, e2, weights
+
+    def forward_packed(self, x1, x2, d1, d2, return_weights=True):
+        """Attention maps of layers after the first differ from the padded formulation on padded QUERY rows only (rows the
+        reference computes from padding and never uses)."""
+        weights = []
+        for i, layer in enumerate(self.cross_attn_layers):
+            x1, x2, w = layer.forward_packed(x1, x2, d1, d2, return_weights, first=i == 0)
+            weights.append(w)
+        return x1, x2, weights
 
 
 def _lin_stack(depth, in_dim, scale=2, norm=None):
@@ -249,12 +345,12 @@ class JointGNN(nn.Module):
             embed = self.protein_gnn(**pg)
         res = self._stack(embed, self.residue_lins, self.residue_norms)
         atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
-        res, rmask = to_dense_batch(res, pg.get("batch"), **hints_p)
-        atm, amask = to_dense_batch(atm, mg.get("batch"), **hints_m)
+        dp = DenseIndex(pg.get("batch"), res.shape[0], device=res.device, **hints_p)
+        dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
         weights = None
         if self.cross_attn_module is not None:
-            res, atm, weights = self.cross_attn_module(res, atm, rmask, amask, self.return_attention)
-        pe, me = self._pool(res, rmask), self._pool(atm, amask)
+            res, atm, weights = self.cross_attn_module.forward_packed(res, atm, dp, dm, self.return_attention)
+        pe, me = self._pool(dp.pad(res), dp.mask), self._pool(dm.pad(atm), dm.mask)
         if self.include_post_pool_layernorm:
             pe, me = self.protein_post_pool_norm(pe), self.molecule_post_pool_norm(me)
         pe = self._stack(self.dropout(self.activation(pe)), self.protein_lins, self.protein_norms)

@@ -129,3 +129,36 @@ def test_synthetic_shapes():
     assert mol["x"].shape[1] == 41 and mol["eattr"].shape[1] == 9 and mol["edge_index"].max() < mol["x"].shape[0]
     ei, nn_ = synth.conv_microbench_graph(3000, k=30)
     assert ei.shape == (2, 3000) and nn_ == 100 and bool((np.diff(ei[0]) >= 0).all())
+
+
+def test_packed_cross_attention_matches_padded_formulation():
+    """The packed-row cross-attention block against the padded nn.MultiheadAttention formulation of the reference
+    (`models/joint_gnn.py:321-408`): outputs on real rows, attention maps everywhere (padded query rows included)."""
+    import torch
+    from caster_dta_b200 import joint
+    torch.manual_seed(4)
+    for d2 in (32, 24):                                   # same / different embedding dims (packed vs split in-proj weights)
+        blk = joint.CrossAttentionModule(32, d2, 4, 0.0, True, 2, 0.0).eval()
+        with torch.no_grad():
+            blk.preattn_norm1.bias.normal_()
+            blk.preattn_norm2.bias.normal_()
+        n1, n2 = [5, 9, 2], [3, 1, 4]
+        b1 = torch.repeat_interleave(torch.arange(3), torch.tensor(n1))
+        b2 = torch.repeat_interleave(torch.arange(3), torch.tensor(n2))
+        x1, x2 = torch.randn(sum(n1), 32), torch.randn(sum(n2), d2)
+        e1, m1 = joint.to_dense_batch(x1, b1)
+        e2, m2 = joint.to_dense_batch(x2, b2)
+        r1, r2, (w1, w2) = blk(e1, e2, m1, m2, True)
+        i1, i2 = joint.DenseIndex(b1, sum(n1)), joint.DenseIndex(b2, sum(n2))
+        p1, p2, (v1, v2) = blk.forward_packed(x1, x2, i1, i2, True)
+        assert torch.allclose(i1.unpad(r1), p1, atol=1e-5) and torch.allclose(i2.unpad(r2), p2, atol=1e-5)
+        assert torch.allclose(w1, v1, atol=1e-6) and torch.allclose(w2, v2, atol=1e-6)
+        q1, q2, _ = blk.forward_packed(x1, x2, i1, i2, False)           # fused SDPA core
+        assert torch.allclose(p1, q1, atol=1e-5) and torch.allclose(p2, q2, atol=1e-5)
+        # gradients through pad / unpad
+        x1g = x1.clone().requires_grad_()
+        blk.forward_packed(x1g, x2, i1, i2, True)[0].square().sum().backward()
+        e1g = x1.clone().requires_grad_()
+        d, _ = joint.to_dense_batch(e1g, b1)
+        (i1.unpad(blk(d, e2, m1, m2, True)[0])).square().sum().backward()
+        assert torch.allclose(x1g.grad, e1g.grad, atol=1e-4)
