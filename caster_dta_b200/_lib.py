@@ -97,6 +97,11 @@ SIGNATURES = {
     "cgvp_featurize_fill": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_attn_supported": (C.c_int32, [C.c_int32, C.c_int32]),
+    "cgvp_attn_fwd": (C.c_int32, [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgvp_attn_bwd": (C.c_int32, [C.c_void_p] * 10 + [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cgvp_node_features": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .encoder import SelectableProteinModelWrapper
 
 
@@ -131,14 +132,18 @@ class DenseIndex:
             self.b, self.m = 1, int(total)
             self.idx = torch.arange(total, device=device)
             self.mask = torch.ones(1, total, dtype=torch.bool, device=device)
+            self.batch = torch.zeros(total, dtype=torch.long, device=device)
+            self.ptr = torch.tensor([0, total], dtype=torch.long, device=device)
             return
         dev = batch.device
         self.b = int(batch[-1]) + 1 if num_graphs is None else int(num_graphs)
         counts = torch.zeros(self.b, dtype=torch.long, device=dev).index_add_(0, batch, torch.ones_like(batch))
-        start = torch.cumsum(counts, 0) - counts
+        self.ptr = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)])           # rows of a graph are contiguous
+        start = self.ptr[:-1]
         self.m = int(counts.max()) if max_nodes is None else int(max_nodes)
         self.idx = batch * self.m + (torch.arange(total, device=dev) - start[batch])
         self.mask = torch.arange(self.m, device=dev).unsqueeze(0) < counts.unsqueeze(1)
+        self.batch = batch.contiguous()
 
     def pad(self, x, fill=None):
         """[total, D] -> [B, max, D]; padding rows hold `fill` ([D]) or zeros."""
@@ -171,11 +176,20 @@ def _mha_packed(mha, q_in, kv_in, dq, dk, q_fill_in, return_weights, training):
     else:
         k, v = F.linear(kv_in, wk, bk), F.linear(kv_in, wv, bv)
     q_fill = F.linear(q_fill_in, wq, bq) if q_fill_in is not None else None
+    p_drop = mha.dropout if training else 0.0
+    if q.is_cuda and p_drop == 0.0 and ops.attention_supported(h, hd):
+        # fused core on packed rows (csrc/attention.cu): no padded tensors, no [B, H, Lq, Lk] scores in HBM
+        o, weights, w_fill = ops.CrossAttnFunction.apply(q, k, v, dq.ptr, dk.ptr, dq.batch, dk.batch, h, dq.m, dk.m,
+                                                         q_fill if return_weights else None, return_weights)
+        if not return_weights:
+            weights = None
+        elif q_fill is not None:
+            weights = torch.where(dq.mask.unsqueeze(-1), weights, w_fill.unsqueeze(1))
+        return mha.out_proj(o), weights
     qd = dq.pad(q, q_fill).view(dq.b, dq.m, h, hd).transpose(1, 2)                 # [B, H, Lq, hd]
     kd = dk.pad(k).view(dk.b, dk.m, h, hd).transpose(1, 2)
     vd = dk.pad(v).view(dk.b, dk.m, h, hd).transpose(1, 2)
     key_mask = dk.mask[:, None, None, :]                                             # True = real key
-    p_drop = mha.dropout if training else 0.0
     weights = None
     if return_weights:
         scores = torch.matmul(qd * (1.0 / hd) ** 0.5, kd.transpose(-2, -1)).masked_fill(~key_mask, float("-inf"))

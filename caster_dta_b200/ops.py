@@ -367,3 +367,55 @@ def segment_reduce(rows, plan, aggr="sum", use_perm=True, out=None, beta=0):
     check(lib().cgvp_segment_reduce(_ptr(rows), width, _ptr(plan.rowptr), _ptr(plan.perm) if use_perm else None, plan.N,
                                     code, int(beta), _ptr(out), _stream()), "cgvp_segment_reduce")
     return out
+
+
+# ---- cross-attention core on packed rows (csrc/attention.cu) ---------------------------------------------------------------
+def attention_supported(num_heads, head_dim):
+    return bool(lib().cgvp_attn_supported(int(num_heads), int(head_dim)))
+
+
+class CrossAttnFunction(torch.autograd.Function):
+    """out, weights = softmax(scale q k^T) v per graph on packed rows; `weights` (head-averaged, padded to
+    [B, lq_max, lk_max]) is not differentiable -- the reference's training loop discards it (`train_model.py:564`)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, qptr, kptr, qbatch, kbatch, num_heads, lq_max, lk_max, q_fill, want_weights):
+        q, k, v = _f32(q), _f32(k), _f32(v)
+        nq, e = q.shape
+        nk, b = k.shape[0], qptr.shape[0] - 1
+        hd = e // num_heads
+        scale = float(hd) ** -0.5
+        dev = q.device
+        out = torch.empty_like(q)
+        stats = torch.empty(nq, num_heads, 2, dtype=torch.float32, device=dev)
+        weights = w_fill = None
+        if want_weights:
+            weights = torch.zeros(b, lq_max, lk_max, dtype=torch.float32, device=dev)
+            if q_fill is not None:
+                q_fill = _f32(q_fill)
+                w_fill = torch.zeros(b, lk_max, dtype=torch.float32, device=dev)
+        _lib.timed_call("cgvp_attn_fwd", lib().cgvp_attn_fwd, _ptr(q), _ptr(k), _ptr(v), _ptr(qptr), _ptr(kptr), _ptr(qbatch), b,
+                        nq, nk, num_heads, hd, scale, _ptr(q_fill) if w_fill is not None else None, int(lq_max), int(lk_max),
+                        _ptr(out), _ptr(stats), _ptr(weights) if weights is not None else None,
+                        _ptr(w_fill) if w_fill is not None else None, _stream())
+        ctx.save_for_backward(q, k, v, out, stats, qptr, kptr, qbatch, kbatch)
+        ctx.num_heads, ctx.scale = num_heads, scale
+        if weights is None:
+            weights = q.new_zeros(0)
+        if w_fill is None:
+            w_fill = q.new_zeros(0)
+        ctx.mark_non_differentiable(weights, w_fill)
+        return out, weights, w_fill
+
+    @staticmethod
+    def backward(ctx, d_out, _dw, _dwf):
+        q, k, v, out, stats, qptr, kptr, qbatch, kbatch = ctx.saved_tensors
+        d_out = _f32(d_out)
+        nq, e = q.shape
+        nk, b = k.shape[0], qptr.shape[0] - 1
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dsum = torch.empty(nq, ctx.num_heads, dtype=torch.float32, device=q.device)
+        _lib.timed_call("cgvp_attn_bwd", lib().cgvp_attn_bwd, _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(stats), _ptr(d_out),
+                        _ptr(qptr), _ptr(kptr), _ptr(qbatch), _ptr(kbatch), b, nq, nk, ctx.num_heads, e // ctx.num_heads,
+                        ctx.scale, _ptr(dsum), _ptr(dq), _ptr(dk), _ptr(dv), _stream())
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None

@@ -229,6 +229,25 @@ int32_t cgvp_node_features(const float* res_coords, const int64_t* ptr, int64_t 
                            const int64_t* idents, const float* aa_table, int32_t num_types, int32_t num_props,
                            int32_t add_posenc, float* out_s, float* out_v, cgvp_stream_t stream);
 
+/* ---- cross-attention core on packed rows ---------------------------------------------------------------------
+ * The scaled-dot-product stage of the two nn.MultiheadAttention modules of CrossAttentionModule
+ * (models/joint_gnn.py:350-361; key_padding_mask = the other side's padding) without padding:
+ *   q:[Nq, H*D]  k, v:[Nk, H*D] fp32 packed rows; graph g owns query rows [qptr[g], qptr[g+1]) and key rows
+ *   [kptr[g], kptr[g+1]); qbatch:[Nq] / kbatch:[Nk] int64 graph id per row.
+ *   out:[Nq, H*D]; stats:[Nq, H, 2] (row max, row sum) for the backward; weights:[B, lq_max, lk_max] (zero-filled
+ *   by the caller) receives the head-averaged probabilities (need_weights=True) or is NULL; q_fill:[H*D] + w_fill:
+ *   [B, lk_max] optionally give the map row of a PADDED query (the reference computes those from padding).
+ * cgvp_attn_bwd recomputes the probabilities and writes dq, dk, dv (dsum:[Nq, H] is scratch).  Deterministic. */
+int32_t cgvp_attn_supported(int32_t num_heads, int32_t head_dim);
+int32_t cgvp_attn_fwd(const float* q, const float* k, const float* v, const int64_t* qptr, const int64_t* kptr,
+                      const int64_t* qbatch, int64_t num_graphs, int64_t num_q, int64_t num_k, int32_t num_heads,
+                      int32_t head_dim, float scale, const float* q_fill, int32_t lq_max, int32_t lk_max, float* out,
+                      float* stats, float* weights, float* w_fill, cgvp_stream_t stream);
+int32_t cgvp_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* stats,
+                      const float* d_out, const int64_t* qptr, const int64_t* kptr, const int64_t* qbatch,
+                      const int64_t* kbatch, int64_t num_graphs, int64_t num_q, int64_t num_k, int32_t num_heads,
+                      int32_t head_dim, float scale, float* dsum, float* dq, float* dk, float* dv, cgvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -303,6 +303,42 @@ def test_protein_graph_batch_feeds_the_encoder():
     assert out.shape == (221, 64) and bool(torch.isfinite(out).all())
 
 
+@pytest.mark.parametrize("heads,hd,nq,nk", [(8, 16, [5, 300, 77], [3, 46, 1]), (4, 8, [9, 1], [30, 200]),
+                                            (8, 16, [40, 21, 3], [700, 333, 990])])
+def test_fused_cross_attention_vs_torch(heads, hd, nq, nk):
+    """csrc/attention.cu against the padded torch formulation (softmax(q k^T / sqrt(d)) v with key padding masks):
+    outputs, head-averaged maps, padded-row fill and all three gradients."""
+    cg = _mods()
+    from caster_dta_b200 import joint, ops
+    g = torch.Generator().manual_seed(sum(nq) + sum(nk))
+    e = heads * hd
+    bq = torch.repeat_interleave(torch.arange(len(nq)), torch.tensor(nq)).to(DEV)
+    bk = torch.repeat_interleave(torch.arange(len(nk)), torch.tensor(nk)).to(DEV)
+    q, k, v = (torch.randn(n, e, generator=g).to(DEV).requires_grad_() for n in (sum(nq), sum(nk), sum(nk)))
+    fill = torch.randn(e, generator=g).to(DEV)
+    cot = torch.randn(sum(nq), e, generator=g).to(DEV)
+    dq_, dk_ = joint.DenseIndex(bq, sum(nq)), joint.DenseIndex(bk, sum(nk))
+    assert ops.attention_supported(heads, hd)
+    out, w, wf = ops.CrossAttnFunction.apply(q, k, v, dq_.ptr, dk_.ptr, dq_.batch, dk_.batch, heads, dq_.m, dk_.m, fill, True)
+    w = torch.where(dq_.mask.unsqueeze(-1), w, wf.unsqueeze(1))
+    grads = torch.autograd.grad((out * cot).sum(), [q, k, v])
+    # reference: padded tensors in fp64
+    q2, k2, v2 = (t.detach().double().requires_grad_() for t in (q, k, v))
+    qd = dq_.pad(q2, fill.double()).view(dq_.b, dq_.m, heads, hd).transpose(1, 2)
+    kd = dk_.pad(k2).view(dk_.b, dk_.m, heads, hd).transpose(1, 2)
+    vd = dk_.pad(v2).view(dk_.b, dk_.m, heads, hd).transpose(1, 2)
+    sc = (qd @ kd.transpose(-2, -1) * hd ** -0.5).masked_fill(~dk_.mask[:, None, None, :], float("-inf"))
+    pr = torch.softmax(sc, -1)
+    ref = dq_.unpad((pr @ vd).transpose(1, 2).reshape(dq_.b, dq_.m, e))
+    rg = torch.autograd.grad((ref * cot.double()).sum(), [q2, k2, v2])
+    assert_close(out, ref, TIGHT, "attention output")
+    assert_close(w, pr.mean(1), TIGHT, "attention map")
+    for a, b, name in zip(grads, rg, ("dq", "dk", "dv")):
+        assert_close(a, b, TIGHT, name)
+    out2, _, _ = ops.CrossAttnFunction.apply(q, k, v, dq_.ptr, dk_.ptr, dq_.batch, dk_.batch, heads, dq_.m, dk_.m, None, False)
+    assert torch.equal(out, out2), "the map output must not change the attention output (and runs must be reproducible)"
+
+
 # ---- oracle comparisons at sizes the golden files do not cover ---------------------------------------------------------
 def _random_layer_case(n, e, nd, ed, seed, hub=False, aggr="sum"):
     from oracle import gvp_oracle
