@@ -102,6 +102,10 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cgvp_attn_bwd": (C.c_int32, [C.c_void_p] * 10 + [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cgvp_linear_wgrad_supported": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32]),
+    "cgvp_linear_wgrad_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "cgvp_linear_wgrad": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "cgvp_node_features": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

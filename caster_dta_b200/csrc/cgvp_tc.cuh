@@ -85,6 +85,28 @@ __device__ __forceinline__ void put8(unsigned char* region, int chunk, int row, 
     q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(region + chunk * PITCH + row * 16) = q;
 }
+// ---- kind::tf32 (split-precision "3xTF32" kernels: gemm_tc.cu, linear_tc.cu) --------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ constexpr uint32_t idesc_tf32(int n) {       // D = f32, A = B = tf32, both K-major, M = 128
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// same with BOTH operands MN-major (the reduction index is the slow one in memory: A^T B products over rows)
+__device__ __forceinline__ constexpr uint32_t idesc_tf32_mn(int n) { return idesc_tf32(n) | (1u << 15) | (1u << 16); }
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MN-major tf32 operands have exactly one legal shared-memory layout, SWIZZLE_128B_BASE32B (layout_type 1): rows of
+// 128 bytes (32 floats of the non-reduced index) per reduction step, 4 steps per 512-byte atom, the 32-byte chunk c of
+// step r stored at chunk c ^ (r & 3); atoms of consecutive steps SBO apart, the next 32 floats LBO apart.
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
 }  // namespace tcx
 using namespace tcx;
 

@@ -29,18 +29,9 @@ struct GemmTcArgs {
     int relu_cols;
 };
 
-__device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ constexpr uint32_t idesc_tf32(int n) {       // D = f32, A = B = tf32, both K-major, M = 128
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
+using tcx::tf32_hi;
+using tcx::idesc_tf32;
+using tcx::mma_tf32;
 
 // W(n, k) = w[n * sn + k * sk]  ->  hi / lo in [k/4][Npad][4], zero padded
 __global__ void gemm_tc_pack_kernel(const float* __restrict__ w, long long sn, long long sk, int N, int K, int Npad, int Kpad,

@@ -1,0 +1,225 @@
+// Weight and bias gradient of a dense layer on the tensor cores, fp32-accurate ("3xTF32"), sm_100a:
+//     dW[N, K] = dY[M, N]^T . X[M, K]        db[N] = sum_m dY[m, :]
+// the autograd of the nn.Linear layers around the GVP encoder (residue / atom stacks, attention projections and
+// feed-forward of models/joint_gnn.py:172-288,321-408), where M = all residues of the batch (~2 x 10^4) and N, K <= 256:
+// a GEMM whose reduction runs over the ROWS of both operands.
+//
+// tcgen05 takes such operands as they lie in memory: both are "MN-major" (the non-reduced index is the contiguous
+// one), staged in the one layout kind::tf32 accepts for that, SWIZZLE_128B_BASE32B -- rows of 32 floats, 4 reduction steps
+// per 512-byte atom, 32-byte chunk c of step r at chunk c ^ (r & 3) -- so a warp copies a row-major tile with coalesced
+// 16-byte loads and conflict-free 16-byte stores, no transposition.  Every fp32 value is split into hi = tf32(x) and lo = x - hi on the way;
+// hi*hi + hi*lo + lo*hi accumulate in fp32 in TMEM (kind::tf32, M = 128 output rows, N = K_in columns, K = 8 rows per MMA).
+// The rows are split over the CTAs (each adds its slab into its own [128, K] TMEM tile and writes a partial), the partials
+// are summed in a fixed order by a second kernel: deterministic.  db rides along: the dY chunks pass through registers.
+#include "cgvp_common.cuh"
+#include "cgvp_tc.cuh"
+
+#define WG_RB 16                          // rows (reduction steps) per stage = 2 MMA k-blocks
+#define WG_GROUP_BYTES (WG_RB * 128)      // one 32-column group of a stage: [4-step atom][4 steps][128 B]
+
+struct WgradArgs {
+    long long M;
+    int N, K;                             // N % 128 == 0, K % 32 == 0, K <= 256
+    const float *dy, *x;
+    float *pw, *pb;                       // partials [S][N][K], [S][N]
+    long long rows_per_cta;
+};
+
+// chunk (r, c): 16 bytes = columns 4c .. 4c+3 of stage row r  ->  byte offset inside an operand tile
+__device__ __forceinline__ int wg_off(int r, int c) {
+    return (c >> 3) * WG_GROUP_BYTES + (r >> 2) * 512 + (r & 3) * 128 + (((((c & 7) >> 1) ^ (r & 3))) << 5) + ((c & 1) << 4);
+}
+__device__ __forceinline__ void wg_split_store(unsigned char* hi, unsigned char* lo, int off, float4 v) {
+    float4 h, l;
+    h.x = tcx::tf32_hi(v.x); h.y = tcx::tf32_hi(v.y); h.z = tcx::tf32_hi(v.z); h.w = tcx::tf32_hi(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+__global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = a.K, KG = K / 32, KC = K / 4;                  // column groups / 16-byte chunks per X row
+    unsigned char* A_hi = smem;
+    unsigned char* A_lo = A_hi + 4 * WG_GROUP_BYTES;
+    unsigned char* B_hi = A_lo + 4 * WG_GROUP_BYTES;
+    unsigned char* B_lo = B_hi + KG * WG_GROUP_BYTES;
+    float* bsm = reinterpret_cast<float*>(B_lo + KG * WG_GROUP_BYTES);          // [4 warps][128] bias staging
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(bsm + 4 * 128);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    const int tmem_cols = K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256));
+    if (tid == 0) { tcx::mbar_init(mbar, 1); tcx::fence_mbar_init(); }
+    if (warp == 0) tcx::tmem_alloc(slot, tmem_cols);
+    tcx::tc_fence_before();
+    __syncthreads();
+    tcx::tc_fence_after();
+    const uint32_t tm0 = *slot;
+
+    const int split = blockIdx.x, mt = blockIdx.y;               // row slab, 128-row tile of dW (= column tile of dY)
+    const long long row_begin = (long long)split * a.rows_per_cta;
+    const long long row_end = min(a.M, row_begin + a.rows_per_cta);
+    const int nstages = (int)((row_end - row_begin + WG_RB - 1) / WG_RB);
+    const float4* dy4 = reinterpret_cast<const float4*>(a.dy);
+    const float4* x4 = reinterpret_cast<const float4*>(a.x);
+    const long long dy_ld4 = a.N / 4;
+    const int c_a = tid & 31;                                    // this thread's dY chunk column (fixed) ...
+    const int r_a = tid >> 5;                                    // ... rows r_a, r_a + 4, r_a + 8, r_a + 12 of a stage
+    const int nb = (WG_RB * KC) / 128;                           // X chunks per thread per stage (KC % 8 == 0 -> exact)
+    float4 ra[4], rb[8];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto load_stage = [&](int st) {
+        const long long r0 = row_begin + (long long)st * WG_RB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = r0 + r_a + 4 * i;
+            ra[i] = r < row_end ? __ldg(dy4 + r * dy_ld4 + mt * 32 + c_a) : zero4;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nb) {
+                const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
+                const long long rr = r0 + r;
+                rb[i] = rr < row_end ? __ldg(x4 + rr * KC + c) : zero4;
+            }
+        }
+    };
+
+    uint32_t phase = 0;
+    if (nstages > 0) load_stage(0);
+    for (int st = 0; st < nstages; ++st) {
+        if (st > 0) { tcx::mbar_wait(mbar, phase); phase ^= 1; }    // the MMAs of the previous stage have read the tiles
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            wg_split_store(A_hi, A_lo, wg_off(r_a + 4 * i, c_a), ra[i]);
+            bsum.x += ra[i].x; bsum.y += ra[i].y; bsum.z += ra[i].z; bsum.w += ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nb) {
+                const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
+                wg_split_store(B_hi, B_lo, wg_off(r, c), rb[i]);
+            }
+        }
+        tcx::fence_proxy_async();
+        tcx::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tcx::tc_fence_after();
+            const uint32_t id = tcx::idesc_tf32_mn(K);
+            const uint32_t ah = tcx::smem_u32(A_hi), al = tcx::smem_u32(A_lo), bh = tcx::smem_u32(B_hi), bl = tcx::smem_u32(B_lo);
+#pragma unroll
+            for (int kb = 0; kb < WG_RB / 8; ++kb) {
+                const uint64_t dah = tcx::smem_desc_mn32(ah + kb * 1024, WG_GROUP_BYTES, 512);
+                const uint64_t dal = tcx::smem_desc_mn32(al + kb * 1024, WG_GROUP_BYTES, 512);
+                const uint64_t dbh = tcx::smem_desc_mn32(bh + kb * 1024, WG_GROUP_BYTES, 512);
+                const uint64_t dbl = tcx::smem_desc_mn32(bl + kb * 1024, WG_GROUP_BYTES, 512);
+                tcx::mma_tf32(tm0, dal, dbh, id, (st > 0 || kb > 0) ? 1u : 0u);      // small terms first
+                tcx::mma_tf32(tm0, dah, dbl, id, 1u);
+                tcx::mma_tf32(tm0, dah, dbh, id, 1u);
+            }
+            tcx::mma_commit(mbar);
+        }
+        if (st + 1 < nstages) load_stage(st + 1);                  // global loads of the next stage fly under the MMAs
+    }
+    if (nstages > 0) { tcx::mbar_wait(mbar, phase); phase ^= 1; }
+    tcx::tc_fence_after();
+    // partial dW tile: TMEM lane = dW row
+    {
+        const uint32_t tm = tm0 + ((uint32_t)(warp * 32) << 16);
+        float* out = a.pw + ((long long)split * a.N + mt * 128 + warp * 32 + lane) * K;
+        for (int c0 = 0; c0 < K; c0 += 16) {
+            float d[16];
+            if (nstages > 0) {
+                tcx::tmem_ld16(tm + c0, d);
+                tcx::tmem_ld_wait(d);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) d[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(out + c0)[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+        }
+    }
+    // partial db: the four warps hold disjoint rows of the same 32 column chunks
+    reinterpret_cast<float4*>(bsm + warp * 128)[lane] = bsum;
+    tcx::tc_fence_before();
+    __syncthreads();
+    if (a.pb && tid < 128) {
+        const float s = bsm[tid] + bsm[128 + tid] + bsm[256 + tid] + bsm[384 + tid];
+        a.pb[(long long)split * a.N + mt * 128 + tid] = s;
+    }
+    if (warp == 0) tcx::tmem_dealloc(tm0, tmem_cols);
+}
+
+__global__ void lin_wgrad_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb, int S, long long nk, int N,
+                                        float* __restrict__ dw, float* __restrict__ db) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nk) {
+        float s = 0.f;
+        for (int p = 0; p < S; ++p) s += pw[(long long)p * nk + i];
+        dw[i] = s;
+    } else if (db && i < nk + N) {
+        const long long n = i - nk;
+        float s = 0.f;
+        for (int p = 0; p < S; ++p) s += pb[(long long)p * N + n];
+        db[n] = s;
+    }
+}
+
+static void wgrad_plan(int64_t M, int32_t N, int* S, long long* rows_per_cta) {
+    const int mt = N / 128;
+    long long s = cgvp_num_sms() / mt;
+    if (s < 1) s = 1;
+    const long long max_s = (M + 63) / 64;                         // at least 4 stages per CTA
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    long long rpc = (M + s - 1) / s;
+    rpc = (rpc + WG_RB - 1) / WG_RB * WG_RB;
+    if (rpc < WG_RB) rpc = WG_RB;
+    *rows_per_cta = rpc;
+    *S = (int)((M + rpc - 1) / rpc);
+    if (*S < 1) *S = 1;
+}
+
+extern "C" int32_t cgvp_linear_wgrad_supported(int64_t M, int32_t N, int32_t K) {
+    return (M >= 1024 && N >= 128 && N % 128 == 0 && N <= 1024 && K >= 32 && K % 32 == 0 && K <= 256) ? 1 : 0;
+}
+
+extern "C" int64_t cgvp_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K) {
+    if (!cgvp_linear_wgrad_supported(M, N, K)) return -1;
+    int S; long long rpc;
+    wgrad_plan(M, N, &S, &rpc);
+    return align_up((int64_t)S * N * K * 4, 256) + align_up((int64_t)S * N * 4, 256) + 256;
+}
+
+static bool wg_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M, int32_t N, int32_t K, float* dw, float* db,
+                                     void* ws, int64_t ws_bytes, void* stream) {
+    CGVP_REQUIRE(cgvp_linear_wgrad_supported(M, N, K), "linear_wgrad: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    CGVP_REQUIRE(dy && x && dw && ws, "linear_wgrad: null argument");
+    CGVP_REQUIRE(wg_al16(dy) && wg_al16(x) && wg_al16(dw), "linear_wgrad: buffers must be 16-byte aligned");
+    CGVP_REQUIRE(ws_bytes >= cgvp_linear_wgrad_workspace_bytes(M, N, K), "linear_wgrad: workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int S; long long rpc;
+    wgrad_plan(M, N, &S, &rpc);
+    char* b = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.N = N; a.K = K; a.dy = dy; a.x = x; a.rows_per_cta = rpc;
+    a.pw = reinterpret_cast<float*>(b);
+    a.pb = reinterpret_cast<float*>(b + align_up((int64_t)S * N * K * 4, 256));
+    const int KG = K / 32;
+    const size_t smem = 1024 + 2 * 4 * WG_GROUP_BYTES + 2 * (size_t)KG * WG_GROUP_BYTES + 4 * 128 * 4 + 64;
+    CGVP_CUDA(cudaFuncSetAttribute(lin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lin_wgrad_kernel<<<dim3((unsigned)S, (unsigned)(N / 128)), 128, smem, st>>>(a);
+    CGVP_LAUNCH_CHECK("lin_wgrad_kernel");
+    const long long nk = (long long)N * K;
+    lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 256), 256, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
+    CGVP_LAUNCH_CHECK("lin_wgrad_reduce_kernel");
+    return 0;
+}

@@ -155,6 +155,17 @@ class DenseIndex:
         return dense.reshape(self.b * self.m, dense.shape[-1]).index_select(0, self.idx)
 
 
+def _lin(mod, x):
+    """nn.Linear applied through ops.linear (tensor-core weight gradient for large row counts on CUDA)."""
+    return ops.linear(x, mod.weight, mod.bias) if x.is_cuda and x.dim() == 2 else mod(x)
+
+
+def _seq(mods, x):
+    for m in mods:
+        x = _lin(m, x) if isinstance(m, nn.Linear) else m(x)
+    return x
+
+
 def _mha_packed(mha, q_in, kv_in, dq, dk, q_fill_in, return_weights, training):
     """`nn.MultiheadAttention.forward(query, key, value, key_padding_mask=~mask)` (`models/joint_gnn.py:350-361`) with
     the in / out projections on packed rows.  q_fill_in: the value every padded QUERY row has in the reference (the
@@ -170,11 +181,12 @@ def _mha_packed(mha, q_in, kv_in, dq, dk, q_fill_in, return_weights, training):
     if mha.in_proj_bias is not None:
         bq, bkv = mha.in_proj_bias[:e], mha.in_proj_bias[e:]
         bk, bv = mha.in_proj_bias[e:2 * e], mha.in_proj_bias[2 * e:]
-    q = F.linear(q_in, wq, bq)
+    lin = ops.linear if q_in.is_cuda else F.linear
+    q = lin(q_in, wq, bq)
     if wkv is not None:
-        k, v = F.linear(kv_in, wkv, bkv).split(e, dim=-1)
+        k, v = lin(kv_in, wkv, bkv).split(e, dim=-1)
     else:
-        k, v = F.linear(kv_in, wk, bk), F.linear(kv_in, wv, bv)
+        k, v = lin(kv_in, wk, bk), lin(kv_in, wv, bv)
     q_fill = F.linear(q_fill_in, wq, bq) if q_fill_in is not None else None
     p_drop = mha.dropout if training else 0.0
     if q.is_cuda and p_drop == 0.0 and ops.attention_supported(h, hd):
@@ -185,7 +197,7 @@ def _mha_packed(mha, q_in, kv_in, dq, dk, q_fill_in, return_weights, training):
             weights = None
         elif q_fill is not None:
             weights = torch.where(dq.mask.unsqueeze(-1), weights, w_fill.unsqueeze(1))
-        return mha.out_proj(o), weights
+        return _lin(mha.out_proj, o), weights
     qd = dq.pad(q, q_fill).view(dq.b, dq.m, h, hd).transpose(1, 2)                 # [B, H, Lq, hd]
     kd = dk.pad(k).view(dk.b, dk.m, h, hd).transpose(1, 2)
     vd = dk.pad(v).view(dk.b, dk.m, h, hd).transpose(1, 2)
@@ -244,9 +256,9 @@ class CrossAttentionModule(nn.Module):
         a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
         if self.include_residual_stream:
             x1 = x1 + self.ff_dropout(a1)
-            x1 = x1 + self.ff_dropout(self.ff1(self.ff_norm1(x1)))
+            x1 = x1 + self.ff_dropout(_seq(self.ff1, self.ff_norm1(x1)))
             x2 = x2 + self.ff_dropout(a2)
-            x2 = x2 + self.ff_dropout(self.ff2(self.ff_norm2(x2)))
+            x2 = x2 + self.ff_dropout(_seq(self.ff2, self.ff_norm2(x2)))
         else:
             x1, x2 = a1, a2
         return x1, x2, (w1, w2)
@@ -336,7 +348,7 @@ class JointGNN(nn.Module):
 
     def _stack(self, x, lins, norms):
         for lin, norm in zip(lins, norms):
-            x = self.dropout(self.activation(norm(lin(x))))
+            x = self.dropout(self.activation(norm(_lin(lin, x))))
         return x
 
     def _pool(self, x, mask):

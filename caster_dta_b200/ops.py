@@ -419,3 +419,50 @@ class CrossAttnFunction(torch.autograd.Function):
                         _ptr(qptr), _ptr(kptr), _ptr(qbatch), _ptr(kbatch), b, nq, nk, ctx.num_heads, e // ctx.num_heads,
                         ctx.scale, _ptr(dsum), _ptr(dq), _ptr(dk), _ptr(dv), _stream())
         return dq, dk, dv, None, None, None, None, None, None, None, None, None
+
+
+# ---- dense layers around the encoder: weight / bias gradient on the tensor cores (csrc/linear_tc.cu) ---------------------
+def linear_wgrad(dy, x, want_bias=True):
+    """(dW [N,K], db [N] or None) = (dy^T x, column sums of dy) for dy [M,N], x [M,K]; fp32-accurate 3xTF32."""
+    dy, x = _f32(dy), _f32(x)
+    m, n = dy.shape
+    k = x.shape[1]
+    dw = torch.empty(n, k, dtype=torch.float32, device=dy.device)
+    db = torch.empty(n, dtype=torch.float32, device=dy.device) if want_bias else None
+    nbytes = lib().cgvp_linear_wgrad_workspace_bytes(m, n, k)
+    ws = _workspace(nbytes, dy.device)
+    wp, wn = _aligned_ptr(ws)
+    _lib.timed_call("cgvp_linear_wgrad", lib().cgvp_linear_wgrad, _ptr(dy), _ptr(x), m, n, k, _ptr(dw), _ptr(db), wp, wn, _stream())
+    return dw, db
+
+
+def linear_wgrad_supported(m, n, k):
+    return bool(lib().cgvp_linear_wgrad_supported(int(m), int(n), int(k)))
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x w^T + b with the stock GEMMs for y and dx and `cgvp_linear_wgrad` for (dw, db)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = linear_wgrad(dy, x, ctx.has_bias)
+        return dx, dw, db
+
+
+def linear(x, w, b=None):
+    """`F.linear` for 2-D CUDA activations; large row counts take the tensor-core weight-gradient path."""
+    if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and torch.is_grad_enabled() and w.requires_grad
+            and linear_wgrad_supported(x.shape[0], w.shape[0], w.shape[1])):
+        return LinearFunction.apply(x, w, b)
+    return torch.nn.functional.linear(x, w, b)

@@ -248,6 +248,16 @@ int32_t cgvp_attn_bwd(const float* q, const float* k, const float* v, const floa
                       const int64_t* kbatch, int64_t num_graphs, int64_t num_q, int64_t num_k, int32_t num_heads,
                       int32_t head_dim, float scale, float* dsum, float* dq, float* dk, float* dv, cgvp_stream_t stream);
 
+/* ---- dense-layer weight / bias gradient on the tensor cores ---------------------------------------------------
+ * dW[N,K] = dY[M,N]^T X[M,K], db[N] = column sums of dY: the autograd of the nn.Linear layers around the encoder
+ * (models/joint_gnn.py:172-288,321-408) for M = all residues of a batch.  fp32-accurate (3xTF32 split precision,
+ * tcgen05 kind::tf32 with MN-major swizzled operands), deterministic.  db may be NULL.  Row-major, contiguous,
+ * 16-byte aligned buffers; supported: M >= 1024, N % 128 == 0 (<= 1024), K % 32 == 0 (<= 256). */
+int32_t cgvp_linear_wgrad_supported(int64_t M, int32_t N, int32_t K);
+int64_t cgvp_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M, int32_t N, int32_t K, float* dw, float* db,
+                          void* ws, int64_t ws_bytes, cgvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

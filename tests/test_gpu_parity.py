@@ -339,6 +339,31 @@ def test_fused_cross_attention_vs_torch(heads, hd, nq, nk):
     assert torch.equal(out, out2), "the map output must not change the attention output (and runs must be reproducible)"
 
 
+@pytest.mark.parametrize("m,n,k", [(1024, 128, 32), (4099, 128, 128), (22806, 256, 128), (20000, 128, 256), (3000, 384, 96)])
+def test_linear_wgrad_tensor_core_vs_fp64(m, n, k):
+    """csrc/linear_tc.cu (3xTF32, MN-major swizzled operands) against an fp64 product: fp32-level accuracy, exact repeat."""
+    _mods()
+    from caster_dta_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    dy = torch.randn(m, n, generator=g).to(DEV)
+    x = (torch.randn(m, k, generator=g) * 3 + 0.5).to(DEV)
+    assert ops.linear_wgrad_supported(m, n, k)
+    dw, db = ops.linear_wgrad(dy, x)
+    ref_w = dy.double().t() @ x.double()
+    ref_b = dy.double().sum(0)
+    assert_close(dw, ref_w, TIGHT, "dW")
+    assert_close(db, ref_b, TIGHT, "db")
+    dw2, db2 = ops.linear_wgrad(dy, x)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    # through autograd
+    w = torch.randn(n, k, generator=g).to(DEV).requires_grad_()
+    b = torch.randn(n, generator=g).to(DEV).requires_grad_()
+    xg = x.clone().requires_grad_()
+    ops.linear(xg, w, b).mul(dy).sum().backward()
+    assert_close(w.grad, ref_w, TIGHT, "dW (autograd)")
+    assert_close(xg.grad, dy.double() @ w.detach().double(), TOL, "dX")
+
+
 # ---- oracle comparisons at sizes the golden files do not cover ---------------------------------------------------------
 def _random_layer_case(n, e, nd, ed, seed, hub=False, aggr="sum"):
     from oracle import gvp_oracle
