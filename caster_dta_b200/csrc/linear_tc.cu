@@ -14,7 +14,7 @@
 #include "cgvp_common.cuh"
 #include "cgvp_tc.cuh"
 
-#define WG_RB 16                          // rows (reduction steps) per stage = 2 MMA k-blocks
+#define WG_RB 32                          // rows (reduction steps) per stage = 4 MMA k-blocks; sets the bytes in flight per CTA
 #define WG_GROUP_BYTES (WG_RB * 128)      // one 32-column group of a stage: [4-step atom][4 steps][128 B]
 
 struct WgradArgs {
@@ -42,15 +42,13 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = a.K, KG = K / 32, KC = K / 4;                  // column groups / 16-byte chunks per X row
-    unsigned char* A_hi = smem;
-    unsigned char* A_lo = A_hi + 4 * WG_GROUP_BYTES;
-    unsigned char* B_hi = A_lo + 4 * WG_GROUP_BYTES;
-    unsigned char* B_lo = B_hi + KG * WG_GROUP_BYTES;
-    float* bsm = reinterpret_cast<float*>(B_lo + KG * WG_GROUP_BYTES);          // [4 warps][128] bias staging
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(bsm + 4 * 128);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    // two stage buffers, each [A_hi | A_lo | B_hi | B_lo]
+    const int stage_bytes = 2 * 4 * WG_GROUP_BYTES + 2 * KG * WG_GROUP_BYTES;
+    float* bsm = reinterpret_cast<float*>(smem + 2 * stage_bytes);             // [4 warps][128] bias staging
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(bsm + 4 * 128);                // [2] one per buffer
+    uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
     const int tmem_cols = K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256));
-    if (tid == 0) { tcx::mbar_init(mbar, 1); tcx::fence_mbar_init(); }
+    if (tid == 0) { tcx::mbar_init(mbar, 1); tcx::mbar_init(mbar + 1, 1); tcx::fence_mbar_init(); }
     if (warp == 0) tcx::tmem_alloc(slot, tmem_cols);
     tcx::tc_fence_before();
     __syncthreads();
@@ -65,21 +63,21 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     const float4* x4 = reinterpret_cast<const float4*>(a.x);
     const long long dy_ld4 = a.N / 4;
     const int c_a = tid & 31;                                    // this thread's dY chunk column (fixed) ...
-    const int r_a = tid >> 5;                                    // ... rows r_a, r_a + 4, r_a + 8, r_a + 12 of a stage
+    const int r_a = tid >> 5;                                    // ... rows r_a, r_a + 4, ... of a stage
     const int nb = (WG_RB * KC) / 128;                           // X chunks per thread per stage (KC % 8 == 0 -> exact)
-    float4 ra[4], rb[8];
+    float4 ra[WG_RB / 4], rb[WG_RB / 2];
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto load_stage = [&](int st) {
         const long long r0 = row_begin + (long long)st * WG_RB;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < WG_RB / 4; ++i) {
             const long long r = r0 + r_a + 4 * i;
             ra[i] = r < row_end ? __ldg(dy4 + r * dy_ld4 + mt * 32 + c_a) : zero4;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < WG_RB / 2; ++i) {
             if (i < nb) {
                 const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
                 const long long rr = r0 + r;
@@ -88,17 +86,22 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
         }
     };
 
-    uint32_t phase = 0;
+    uint32_t phase[2] = {0, 0};
     if (nstages > 0) load_stage(0);
     for (int st = 0; st < nstages; ++st) {
-        if (st > 0) { tcx::mbar_wait(mbar, phase); phase ^= 1; }    // the MMAs of the previous stage have read the tiles
+        const int buf = st & 1;
+        unsigned char* A_hi = smem + buf * stage_bytes;
+        unsigned char* A_lo = A_hi + 4 * WG_GROUP_BYTES;
+        unsigned char* B_hi = A_lo + 4 * WG_GROUP_BYTES;
+        unsigned char* B_lo = B_hi + KG * WG_GROUP_BYTES;
+        if (st >= 2) { tcx::mbar_wait(mbar + buf, phase[buf]); phase[buf] ^= 1; }   // the MMAs of stage st-2 have read this buffer
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < WG_RB / 4; ++i) {
             wg_split_store(A_hi, A_lo, wg_off(r_a + 4 * i, c_a), ra[i]);
             bsum.x += ra[i].x; bsum.y += ra[i].y; bsum.z += ra[i].z; bsum.w += ra[i].w;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < WG_RB / 2; ++i) {
             if (i < nb) {
                 const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
                 wg_split_store(B_hi, B_lo, wg_off(r, c), rb[i]);
@@ -121,11 +124,13 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
                 tcx::mma_tf32(tm0, dah, dbl, id, 1u);
                 tcx::mma_tf32(tm0, dah, dbh, id, 1u);
             }
-            tcx::mma_commit(mbar);
+            tcx::mma_commit(mbar + buf);
         }
         if (st + 1 < nstages) load_stage(st + 1);                  // global loads of the next stage fly under the MMAs
     }
-    if (nstages > 0) { tcx::mbar_wait(mbar, phase); phase ^= 1; }
+    // the last commit on each buffer covers every earlier MMA (commits complete in order)
+    if (nstages > 0) { const int b = (nstages - 1) & 1; tcx::mbar_wait(mbar + b, phase[b]); phase[b] ^= 1; }
+    if (nstages > 1) { const int b = (nstages - 2) & 1; tcx::mbar_wait(mbar + b, phase[b]); phase[b] ^= 1; }
     tcx::tc_fence_after();
     // partial dW tile: TMEM lane = dW row
     {
@@ -155,19 +160,25 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     if (warp == 0) tcx::tmem_dealloc(tm0, tmem_cols);
 }
 
+// fixed-order sum of the S partials (four interleaved chains, combined at the end: always the same association)
+__device__ __forceinline__ float wg_sum_partials(const float* __restrict__ p, long long stride, int S) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int q = 0;
+#pragma unroll 2
+    for (; q + 3 < S; q += 4) {
+        s0 += __ldg(p + (long long)q * stride);
+        s1 += __ldg(p + (long long)(q + 1) * stride);
+        s2 += __ldg(p + (long long)(q + 2) * stride);
+        s3 += __ldg(p + (long long)(q + 3) * stride);
+    }
+    for (; q < S; ++q) s0 += __ldg(p + (long long)q * stride);
+    return (s0 + s1) + (s2 + s3);
+}
 __global__ void lin_wgrad_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb, int S, long long nk, int N,
                                         float* __restrict__ dw, float* __restrict__ db) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nk) {
-        float s = 0.f;
-        for (int p = 0; p < S; ++p) s += pw[(long long)p * nk + i];
-        dw[i] = s;
-    } else if (db && i < nk + N) {
-        const long long n = i - nk;
-        float s = 0.f;
-        for (int p = 0; p < S; ++p) s += pb[(long long)p * N + n];
-        db[n] = s;
-    }
+    if (i < nk) dw[i] = wg_sum_partials(pw + i, nk, S);
+    else if (db && i < nk + N) db[i - nk] = wg_sum_partials(pb + (i - nk), N, S);
 }
 
 static void wgrad_plan(int64_t M, int32_t N, int* S, long long* rows_per_cta) {
@@ -214,12 +225,208 @@ extern "C" int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M,
     a.pw = reinterpret_cast<float*>(b);
     a.pb = reinterpret_cast<float*>(b + align_up((int64_t)S * N * K * 4, 256));
     const int KG = K / 32;
-    const size_t smem = 1024 + 2 * 4 * WG_GROUP_BYTES + 2 * (size_t)KG * WG_GROUP_BYTES + 4 * 128 * 4 + 64;
+    const size_t smem = 1024 + 2 * (2 * 4 * WG_GROUP_BYTES + 2 * (size_t)KG * WG_GROUP_BYTES) + 4 * 128 * 4 + 64;
     CGVP_CUDA(cudaFuncSetAttribute(lin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lin_wgrad_kernel<<<dim3((unsigned)S, (unsigned)(N / 128)), 128, smem, st>>>(a);
     CGVP_LAUNCH_CHECK("lin_wgrad_kernel");
     const long long nk = (long long)N * K;
-    lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 256), 256, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
+    lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 128), 128, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
     CGVP_LAUNCH_CHECK("lin_wgrad_reduce_kernel");
     return 0;
+}
+
+// ---- forward / input-gradient GEMM ------------------------------------------------------------------------------------------
+//     Y[M, N] = A[M, K] . B[N, K]^T (+ bias),   B(n, k) = w[n * sn + k * sk]
+// forward: A = x, B = weight (sn = K, sk = 1);  input gradient: A = dY, B = weight^T (sn = 1, sk = in_features).
+// Persistent CTAs (one per SM): the CTA's NT-column slice of B is split (hi / lo tf32) ONCE into shared memory in the K-major
+// core-matrix layout [k/4][n][4] and stays there; 128-row tiles of A stream through two 32-column staging buffers (global
+// loads prefetched into registers while the previous chunk's MMAs run, split, stored), 12 kind::tf32 MMAs per chunk into one
+// TMEM accumulator, epilogue (bias, store) per tile.  Same 3xTF32 arithmetic as gemm_tc.cu.
+#define LG_KC 32
+#define LG_LBO_A (2048 + 16)             // +16: the 8 k4 slices of a row land in 8 different bank groups
+
+struct LinGemmArgs {
+    long long M;
+    int N, K, NT;                          // K % 32 == 0, N % NT == 0, NT % 16 == 0
+    const float *A, *w, *bias;
+    long long sn, sk;
+    float* Y;
+};
+
+__global__ void __launch_bounds__(128, 1) lin_gemm_kernel(const __grid_constant__ LinGemmArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NT = a.NT, K = a.K, nchunks = K / LG_KC;
+    const int b_lbo = NT * 16;                                            // bytes between k4 slices of B
+    unsigned char* B_hi = smem;
+    unsigned char* B_lo = B_hi + (size_t)(K / 4) * b_lbo;
+    unsigned char* A_buf = B_lo + (size_t)(K / 4) * b_lbo;                // [2 buffers][hi, lo][8 k4 slices][LG_LBO_A]
+    uint64_t* abar = reinterpret_cast<uint64_t*>(A_buf + 2 * 2 * 8 * LG_LBO_A);
+    uint64_t* dbar = abar + 2;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(dbar + 1);
+    const int tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+    if (tid == 0) { tcx::mbar_init(abar, 1); tcx::mbar_init(abar + 1, 1); tcx::mbar_init(dbar, 1); tcx::fence_mbar_init(); }
+    if (warp == 0) tcx::tmem_alloc(slot, tmem_cols);
+    const int n0 = blockIdx.y * NT;
+    // B slice -> shared memory, split.  Lanes run along the contiguous index of w (k for the forward use, n for the
+    // transposed use); 8 independent loads in flight per thread.
+    {
+        const int total = NT * (K / 4), K4 = K / 4;
+        const bool k_contig = a.sk == 1;
+        for (int i0 = tid; i0 < total; i0 += 128 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 128;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) {
+                    const int n = k_contig ? i / K4 : i % NT, k4 = k_contig ? i % K4 : i / NT;
+                    const float* p = a.w + (long long)(n0 + n) * a.sn + (long long)(4 * k4) * a.sk;
+                    if (k_contig) v[u] = __ldg(reinterpret_cast<const float4*>(p));
+                    else { v[u].x = __ldg(p); v[u].y = __ldg(p + a.sk); v[u].z = __ldg(p + 2 * a.sk); v[u].w = __ldg(p + 3 * a.sk); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 128;
+                if (i < total) {
+                    const int n = k_contig ? i / K4 : i % NT, k4 = k_contig ? i % K4 : i / NT;
+                    const float4 h = make_float4(tcx::tf32_hi(v[u].x), tcx::tf32_hi(v[u].y), tcx::tf32_hi(v[u].z), tcx::tf32_hi(v[u].w));
+                    *reinterpret_cast<float4*>(B_hi + k4 * b_lbo + n * 16) = h;
+                    *reinterpret_cast<float4*>(B_lo + k4 * b_lbo + n * 16) = make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w);
+                }
+            }
+        }
+    }
+    tcx::fence_proxy_async();
+    tcx::tc_fence_before();
+    __syncthreads();
+    tcx::tc_fence_after();
+    const uint32_t tm0 = *slot;
+    const uint32_t tm = tm0 + ((uint32_t)(warp * 32) << 16);
+    const uint32_t id = tcx::idesc_tf32(NT);
+    const long long ntiles = (a.M + 127) / 128;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 regs[8];
+    auto load_chunk = [&](long long tile, int c) {                        // 128 rows x 32 floats: lane -> (row, k4), k4 fastest
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = tid + q * 128, r = i >> 3, k4 = i & 7;
+            const long long m = tile * 128 + r;
+            regs[q] = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + m * K + c * LG_KC) + k4) : zero4;
+        }
+    };
+    uint32_t pa[2] = {0, 0}, pd = 0;
+    int used[2] = {0, 0};                                                 // buffer holds operands of MMAs not yet known complete
+    long long tile = blockIdx.x;
+    if (tile < ntiles) load_chunk(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+            const int buf = c & 1;
+            unsigned char* Ah = A_buf + (size_t)buf * 2 * 8 * LG_LBO_A;
+            unsigned char* Al = Ah + 8 * LG_LBO_A;
+            if (used[buf]) { tcx::mbar_wait(abar + buf, pa[buf]); pa[buf] ^= 1; used[buf] = 0; }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = tid + q * 128, r = i >> 3, k4 = i & 7;
+                const float4 x = regs[q];
+                const float4 h = make_float4(tcx::tf32_hi(x.x), tcx::tf32_hi(x.y), tcx::tf32_hi(x.z), tcx::tf32_hi(x.w));
+                *reinterpret_cast<float4*>(Ah + k4 * LG_LBO_A + r * 16) = h;
+                *reinterpret_cast<float4*>(Al + k4 * LG_LBO_A + r * 16) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+            tcx::fence_proxy_async();
+            tcx::tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tcx::tc_fence_after();
+                const uint32_t ah = tcx::smem_u32(Ah), al = tcx::smem_u32(Al);
+                const uint32_t bh = tcx::smem_u32(B_hi) + (uint32_t)(c * 8 * b_lbo), bl = tcx::smem_u32(B_lo) + (uint32_t)(c * 8 * b_lbo);
+#pragma unroll
+                for (int k8 = 0; k8 < LG_KC / 8; ++k8) {
+                    const uint64_t dah = tcx::smem_desc(ah + k8 * 2 * LG_LBO_A, LG_LBO_A), dal = tcx::smem_desc(al + k8 * 2 * LG_LBO_A, LG_LBO_A);
+                    const uint64_t dbh = tcx::smem_desc(bh + k8 * 2 * b_lbo, b_lbo), dbl = tcx::smem_desc(bl + k8 * 2 * b_lbo, b_lbo);
+                    tcx::mma_tf32(tm0, dal, dbh, id, (c | k8) != 0);
+                    tcx::mma_tf32(tm0, dah, dbl, id, 1);
+                    tcx::mma_tf32(tm0, dah, dbh, id, 1);
+                }
+                tcx::mma_commit(abar + buf);
+                if (c == nchunks - 1) tcx::mma_commit(dbar);
+            }
+            used[buf] = 1;
+            // next chunk (possibly of the next tile) into registers while the tensor pipe works
+            if (c + 1 < nchunks) load_chunk(tile, c + 1);
+            else if (tile + gridDim.x < ntiles) load_chunk(tile + gridDim.x, 0);
+        }
+        tcx::mbar_wait(dbar, pd);
+        pd ^= 1;
+        tcx::tc_fence_after();
+        const long long m = tile * 128 + tid;
+        for (int cb = 0; cb < NT; cb += 16) {
+            float d[16];
+            tcx::tmem_ld16(tm + cb, d);
+            tcx::tmem_ld_wait(d);
+            if (m < a.M) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int n = n0 + cb + 4 * j4;
+                    float4 v = make_float4(d[4 * j4], d[4 * j4 + 1], d[4 * j4 + 2], d[4 * j4 + 3]);
+                    if (a.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    }
+                    *reinterpret_cast<float4*>(a.Y + m * a.N + n) = v;
+                }
+            }
+        }
+        tcx::tc_fence_before();
+        __syncthreads();                                                  // TMEM reads done before the next tile overwrites it
+        tcx::tc_fence_after();
+    }
+    // drain the per-buffer barriers (the last tile's commits) -- all covered by dbar, nothing to wait for
+    tcx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tcx::tmem_dealloc(tm0, tmem_cols);
+}
+
+static int lin_gemm_nt(int N, int K) {
+    int nt = N < 128 ? N : 128;
+    while (nt > 16 && ((long long)K * nt * 8 > 131072 || N % nt != 0)) nt -= 16;
+    return nt;
+}
+
+extern "C" int32_t cgvp_linear_gemm_supported(int64_t M, int32_t N, int32_t K) {
+    if (!(M >= 1024 && N >= 16 && N % 16 == 0 && N <= 4096 && K >= 32 && K % 32 == 0 && K <= 1024)) return 0;
+    const int nt = lin_gemm_nt(N, K);
+    return (nt >= 16 && N % nt == 0 && (long long)K * nt * 8 <= 131072) ? 1 : 0;
+}
+
+static int lin_gemm_launch(const float* A, const float* w, long long sn, long long sk, const float* bias, int64_t M, int32_t N,
+                           int32_t K, float* Y, cudaStream_t st) {
+    CGVP_REQUIRE(cgvp_linear_gemm_supported(M, N, K), "linear_gemm: unsupported shape M=%lld N=%d K=%d", (long long)M, N, K);
+    CGVP_REQUIRE(A && w && Y, "linear_gemm: null argument");
+    CGVP_REQUIRE(wg_al16(A) && wg_al16(Y) && wg_al16(bias) && wg_al16(w), "linear_gemm: buffers must be 16-byte aligned");
+    LinGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.N = N; a.K = K; a.NT = lin_gemm_nt(N, K); a.A = A; a.w = w; a.bias = bias; a.sn = sn; a.sk = sk; a.Y = Y;
+    const size_t smem = 128 + 2 * (size_t)(K / 4) * a.NT * 16 + 2 * 2 * 8 * LG_LBO_A + 64;
+    CGVP_CUDA(cudaFuncSetAttribute(lin_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntile_n = N / a.NT;
+    long long gx = cgvp_num_sms() / ntile_n;
+    if (gx < 1) gx = 1;
+    const long long mtiles = (M + 127) / 128;
+    if (gx > mtiles) gx = mtiles;
+    lin_gemm_kernel<<<dim3((unsigned)gx, (unsigned)ntile_n), 128, smem, st>>>(a);
+    CGVP_LAUNCH_CHECK("lin_gemm_kernel");
+    return 0;
+}
+
+// y[M, N] = x[M, K] w[N, K]^T + bias         (nn.Linear forward)
+extern "C" int32_t cgvp_linear_fwd(const float* x, const float* w, const float* bias, int64_t M, int32_t N, int32_t K, float* y,
+                                   void* stream) {
+    return lin_gemm_launch(x, w, K, 1, bias, M, N, K, y, reinterpret_cast<cudaStream_t>(stream));
+}
+// dx[M, K] = dy[M, N] w[N, K]                (nn.Linear input gradient)
+extern "C" int32_t cgvp_linear_dgrad(const float* dy, const float* w, int64_t M, int32_t N, int32_t K, float* dx, void* stream) {
+    return lin_gemm_launch(dy, w, 1, K, nullptr, M, K, N, dx, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -440,20 +440,53 @@ def linear_wgrad_supported(m, n, k):
     return bool(lib().cgvp_linear_wgrad_supported(int(m), int(n), int(k)))
 
 
+# The forward / input-gradient GEMMs of csrc/linear_tc.cu are correct (fp32-accurate) but at the ~1 GFLOP sizes of this model
+# they take ~30 us against ~16 us for the stock SIMT GEMM (the per-CTA weight-slice load is amortised over 1-2 row tiles), so
+# they are opt-in; the weight-gradient kernel (3x faster than the stock path) is always on.
+USE_TC_LINEAR_GEMM = False
+
+
+def linear_gemm_supported(m, out_cols, red_len):
+    return USE_TC_LINEAR_GEMM and bool(lib().cgvp_linear_gemm_supported(int(m), int(out_cols), int(red_len)))
+
+
+def _linear_fwd(x, w, b):
+    m, k = x.shape
+    n = w.shape[0]
+    if not linear_gemm_supported(m, n, k):
+        return torch.nn.functional.linear(x, w, b)
+    x, w, b = _f32(x), _f32(w), _f32(b)
+    y = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    _lib.timed_call("cgvp_linear_fwd", lib().cgvp_linear_fwd, _ptr(x), _ptr(w), _ptr(b), m, n, k, _ptr(y), _stream())
+    return y
+
+
+def _linear_dgrad(dy, w):
+    m, n = dy.shape
+    k = w.shape[1]
+    if not linear_gemm_supported(m, k, n):
+        return dy @ w
+    dy, w = _f32(dy), _f32(w)
+    dx = torch.empty(m, k, dtype=torch.float32, device=dy.device)
+    _lib.timed_call("cgvp_linear_dgrad", lib().cgvp_linear_dgrad, _ptr(dy), _ptr(w), m, n, k, _ptr(dx), _stream())
+    return dx
+
+
 class LinearFunction(torch.autograd.Function):
-    """y = x w^T + b with the stock GEMMs for y and dx and `cgvp_linear_wgrad` for (dw, db)."""
+    """y = x w^T + b on the tensor cores with fp32 accuracy (3xTF32, csrc/linear_tc.cu): forward, input gradient and
+    weight / bias gradient; shapes outside the kernels' range fall back to the stock GEMMs."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        return torch.nn.functional.linear(x, w, b)
+        return _linear_fwd(x, w, b)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dx = _linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = linear_wgrad(dy, x, ctx.has_bias)
@@ -462,7 +495,11 @@ class LinearFunction(torch.autograd.Function):
 
 def linear(x, w, b=None):
     """`F.linear` for 2-D CUDA activations; large row counts take the tensor-core weight-gradient path."""
-    if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and torch.is_grad_enabled() and w.requires_grad
-            and linear_wgrad_supported(x.shape[0], w.shape[0], w.shape[1])):
-        return LinearFunction.apply(x, w, b)
+    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and w.dtype == torch.float32:
+        m, n, k = x.shape[0], w.shape[0], w.shape[1]
+        if torch.is_grad_enabled() and (w.requires_grad or x.requires_grad):
+            if linear_wgrad_supported(m, n, k):
+                return LinearFunction.apply(x.contiguous(), w, b)
+        elif linear_gemm_supported(m, n, k):
+            return _linear_fwd(x.contiguous(), w, b)
     return torch.nn.functional.linear(x, w, b)

@@ -257,6 +257,13 @@ int32_t cgvp_linear_wgrad_supported(int64_t M, int32_t N, int32_t K);
 int64_t cgvp_linear_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
 int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M, int32_t N, int32_t K, float* dw, float* db,
                           void* ws, int64_t ws_bytes, cgvp_stream_t stream);
+/* y[M,N] = x[M,K] w[N,K]^T + bias (nn.Linear forward) and dx[M,K] = dy[M,N] w[N,K] (its input gradient), same 3xTF32
+ * arithmetic, persistent CTAs with the weight slice resident in shared memory.  cgvp_linear_gemm_supported(M, out, in)
+ * answers for y = A B^T with `out` result columns and `in` reduction length (forward: (M, N, K); dgrad: (M, K, N)). */
+int32_t cgvp_linear_gemm_supported(int64_t M, int32_t out_cols, int32_t red_len);
+int32_t cgvp_linear_fwd(const float* x, const float* w, const float* bias, int64_t M, int32_t N, int32_t K, float* y,
+                        cgvp_stream_t stream);
+int32_t cgvp_linear_dgrad(const float* dy, const float* w, int64_t M, int32_t N, int32_t K, float* dx, cgvp_stream_t stream);
 
 #ifdef __cplusplus
 }

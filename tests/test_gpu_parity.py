@@ -359,9 +359,17 @@ def test_linear_wgrad_tensor_core_vs_fp64(m, n, k):
     w = torch.randn(n, k, generator=g).to(DEV).requires_grad_()
     b = torch.randn(n, generator=g).to(DEV).requires_grad_()
     xg = x.clone().requires_grad_()
-    ops.linear(xg, w, b).mul(dy).sum().backward()
+    prev, ops.USE_TC_LINEAR_GEMM = ops.USE_TC_LINEAR_GEMM, True       # also exercise the opt-in forward / dgrad kernels
+    try:
+        y = ops.linear(xg, w, b)
+        y.mul(dy).sum().backward()
+        with torch.no_grad():
+            assert torch.equal(ops.linear(x, w, b), y), "inference path = training forward"
+    finally:
+        ops.USE_TC_LINEAR_GEMM = prev
+    assert_close(y, x.double() @ w.detach().double().t() + b.detach().double(), TIGHT, "y")
     assert_close(w.grad, ref_w, TIGHT, "dW (autograd)")
-    assert_close(xg.grad, dy.double() @ w.detach().double(), TOL, "dX")
+    assert_close(xg.grad, dy.double() @ w.detach().double(), TIGHT, "dX")
 
 
 # ---- oracle comparisons at sizes the golden files do not cover ---------------------------------------------------------
