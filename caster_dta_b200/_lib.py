@@ -109,6 +109,12 @@ SIGNATURES = {
     "cgvp_linear_gemm_supported": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32]),
     "cgvp_linear_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cgvp_linear_dgrad": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cgvp_layernorm_supported": (C.c_int32, [C.c_int32]),
+    "cgvp_layernorm_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "cgvp_layernorm_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "cgvp_layernorm_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cgvp_node_features": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -249,16 +249,16 @@ class CrossAttentionModule(nn.Module):
 
     def forward_packed(self, x1, x2, d1, d2, return_weights=True, first=True):
         """Same block (`models/joint_gnn.py:321-408`) on packed rows x1 [N1, D1], x2 [N2, D2]; d1 / d2: DenseIndex."""
-        n1, n2 = self.preattn_norm1(x1), self.preattn_norm2(x2)
+        n1, n2 = ops.layer_norm(x1, self.preattn_norm1), ops.layer_norm(x2, self.preattn_norm2)
         f1 = self.preattn_norm1.bias if first else None
         f2 = self.preattn_norm2.bias if first else None
         a1, w1 = _mha_packed(self.embed1_to_2, n1, n2, d1, d2, f1, return_weights, self.training)
         a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
         if self.include_residual_stream:
             x1 = x1 + self.ff_dropout(a1)
-            x1 = x1 + self.ff_dropout(_seq(self.ff1, self.ff_norm1(x1)))
+            x1 = x1 + self.ff_dropout(_seq(self.ff1, ops.layer_norm(x1, self.ff_norm1)))
             x2 = x2 + self.ff_dropout(a2)
-            x2 = x2 + self.ff_dropout(_seq(self.ff2, self.ff_norm2(x2)))
+            x2 = x2 + self.ff_dropout(_seq(self.ff2, ops.layer_norm(x2, self.ff_norm2)))
         else:
             x1, x2 = a1, a2
         return x1, x2, (w1, w2)

@@ -503,3 +503,37 @@ def linear(x, w, b=None):
         elif linear_gemm_supported(m, n, k):
             return _linear_fwd(x.contiguous(), w, b)
     return torch.nn.functional.linear(x, w, b)
+
+
+# ---- row LayerNorm on packed activations (csrc/layernorm.cu) ---------------------------------------------------------------
+class LayerNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x, g, b = _f32(x), _f32(gamma), _f32(beta)
+        rows, d = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+        _lib.timed_call("cgvp_layernorm_fwd", lib().cgvp_layernorm_fwd, _ptr(x), _ptr(g), _ptr(b), rows, d, float(eps), _ptr(y),
+                        _ptr(stats), _stream())
+        ctx.save_for_backward(x, g, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, stats = ctx.saved_tensors
+        dy = _f32(dy)
+        rows, d = x.shape
+        dx, dg, db = torch.empty_like(x), torch.empty_like(g), torch.empty_like(g)
+        ws = _workspace(lib().cgvp_layernorm_workspace_bytes(rows, d), x.device)
+        wp, wn = _aligned_ptr(ws)
+        _lib.timed_call("cgvp_layernorm_bwd", lib().cgvp_layernorm_bwd, _ptr(dy), _ptr(x), _ptr(stats), _ptr(g), rows, d, _ptr(dx),
+                        _ptr(dg), _ptr(db), wp, wn, _stream())
+        return dx, dg, db, None
+
+
+def layer_norm(x, mod):
+    """`mod(x)` for an affine nn.LayerNorm over the last dimension of packed 2-D CUDA activations."""
+    if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and mod.elementwise_affine and mod.bias is not None
+            and len(mod.normalized_shape) == 1 and x.shape[0] > 0 and lib().cgvp_layernorm_supported(int(x.shape[1]))):
+        return LayerNormFunction.apply(x, mod.weight, mod.bias, mod.eps)
+    return mod(x)

@@ -265,6 +265,17 @@ int32_t cgvp_linear_fwd(const float* x, const float* w, const float* bias, int64
                         cgvp_stream_t stream);
 int32_t cgvp_linear_dgrad(const float* dy, const float* w, int64_t M, int32_t N, int32_t K, float* dx, cgvp_stream_t stream);
 
+/* ---- row LayerNorm --------------------------------------------------------------------------------------------
+ * nn.LayerNorm(D) (eps inside the square root, affine) on packed [rows, D] activations, D in {32, 64, 128, 256}: the
+ * preattn_norm / ff_norm layers of CrossAttentionModule (models/joint_gnn.py:321-408).  stats:[rows, 2] = (mean, rstd).
+ * The backward writes dx and the gamma / beta gradients (per-CTA partials summed in a fixed order: deterministic). */
+int32_t cgvp_layernorm_supported(int32_t D);
+int64_t cgvp_layernorm_workspace_bytes(int64_t rows, int32_t D);
+int32_t cgvp_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t D, float eps,
+                           float* y, float* stats, cgvp_stream_t stream);
+int32_t cgvp_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, int64_t rows, int32_t D,
+                           float* dx, float* dgamma, float* dbeta, void* ws, int64_t ws_bytes, cgvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,6 +372,33 @@ def test_linear_wgrad_tensor_core_vs_fp64(m, n, k):
     assert_close(xg.grad, dy.double() @ w.detach().double(), TIGHT, "dX")
 
 
+@pytest.mark.parametrize("rows,d", [(1, 32), (1000, 128), (22806, 128), (4097, 256), (333, 64)])
+def test_row_layernorm_vs_torch(rows, d):
+    """csrc/layernorm.cu against nn.LayerNorm in fp64: output, dx, dgamma, dbeta; bit-reproducible."""
+    _mods()
+    from caster_dta_b200 import ops
+    g = torch.Generator().manual_seed(rows + d)
+    ln = torch.nn.LayerNorm(d).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(d, generator=g)); ln.bias.copy_(torch.randn(d, generator=g))
+    x = (torch.randn(rows, d, generator=g) * 2 + 0.3).to(DEV).requires_grad_()
+    cot = torch.randn(rows, d, generator=g).to(DEV)
+    y = ops.layer_norm(x, ln)
+    gx, gw, gb = torch.autograd.grad((y * cot).sum(), [x, ln.weight, ln.bias])
+    ref = torch.nn.LayerNorm(d).double().to(DEV)
+    ref.load_state_dict({k: v.double() for k, v in ln.state_dict().items()})
+    x2 = x.detach().double().requires_grad_()
+    y2 = ref(x2)
+    rx, rw, rb = torch.autograd.grad((y2 * cot.double()).sum(), [x2, ref.weight, ref.bias])
+    assert_close(y, y2, TIGHT, "y")
+    assert_close(gx, rx, TIGHT, "dx")
+    assert_close(gw, rw, TIGHT, "dgamma")
+    assert_close(gb, rb, TIGHT, "dbeta")
+    y3 = ops.layer_norm(x, ln)
+    g3 = torch.autograd.grad((y3 * cot).sum(), [x, ln.weight, ln.bias])
+    assert torch.equal(y, y3) and all(torch.equal(a, b) for a, b in zip((gx, gw, gb), g3))
+
+
 # ---- oracle comparisons at sizes the golden files do not cover ---------------------------------------------------------
 def _random_layer_case(n, e, nd, ed, seed, hub=False, aggr="sum"):
     from oracle import gvp_oracle
