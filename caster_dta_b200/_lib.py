@@ -87,6 +87,12 @@ SIGNATURES = {
     "cgvp_conv_bwd": (C.c_int32, [C.POINTER(ConvDesc), C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p]),
+    "cgvp_conv_stash_bytes": (C.c_int64, [C.POINTER(ConvDesc), C.c_int64]),
+    "cgvp_conv_fwd_stash": (C.c_int32, [C.POINTER(ConvDesc), C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cgvp_conv_bwd_stash": (C.c_int32, [C.POINTER(ConvDesc), C.POINTER(Plan), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cgvp_rows_workspace_bytes": (C.c_int64, [C.POINTER(RowDesc), C.c_int64, C.c_int32]),
     "cgvp_rows_fwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.c_void_p, C.c_int64, C.c_void_p]),
     "cgvp_rows_bwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.POINTER(RowGradArgs), C.c_void_p,

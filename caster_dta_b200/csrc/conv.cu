@@ -7,11 +7,13 @@ using namespace cgvp;
 
 int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, float* out_s, float* out_v, float* part_head,
-                     float* part_tail, cudaStream_t st, int* rc_out);
+                     float* part_tail, float* stash, cudaStream_t st, int* rc_out);
+int64_t conv_special_stash_floats(const CgvpConvDesc* desc);
 int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, const float* d_out_s, const float* d_out_v,
                      float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
-                     float* part_tail, float* dj, float* partial, int max_grid, cudaStream_t st, int* grid_out, int* rc_out);
+                     float* part_tail, float* dj, float* partial, int max_grid, const float* stash, cudaStream_t st, int* grid_out,
+                     int* rc_out);
 
 int64_t conv_tc_workspace_bytes(const CgvpConvDesc* desc, int64_t E, int64_t N);
 int conv_fwd_tc(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
@@ -456,9 +458,20 @@ static int conv_common_checks(const ConvK& K, const CgvpPlan* plan, const float*
     return 0;
 }
 
+extern "C" int64_t cgvp_conv_stash_bytes(const CgvpConvDesc* desc, int64_t num_edges) {
+    if (!desc || num_edges <= 0) return 0;
+    return conv_special_stash_floats(desc) * num_edges * 4;
+}
+
 extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
                                  const float* e_s, const float* e_v, const float* const* h_packed, float* out_s,
                                  float* out_v, void* ws, int64_t ws_bytes, cgvp_stream_t stream) {
+    return cgvp_conv_fwd_stash(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int32_t cgvp_conv_fwd_stash(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
+                                       const float* e_s, const float* e_v, const float* const* h_packed, float* out_s,
+                                       float* out_v, void* ws, int64_t ws_bytes, void* stash, cgvp_stream_t stream) {
     ConvK K;
     if (build_conv_k(desc, false, K)) return -1;
     if (conv_common_checks(K, plan, x_s, x_v, e_s, e_v, h_packed)) return -1;
@@ -473,7 +486,7 @@ extern "C" int32_t cgvp_conv_fwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
             int rc = 0;
             if (conv_fwd_tc(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, base + need, ws_bytes - need, st, &rc)) return rc;
             if (conv_fwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, reinterpret_cast<float*>(base + oh),
-                                 reinterpret_cast<float*>(base + ot), st, &rc))
+                                 reinterpret_cast<float*>(base + ot), reinterpret_cast<float*>(stash), st, &rc))
                 return rc;
         }
     }
@@ -521,6 +534,15 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
                                  const float* d_out_v, float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v,
                                  int32_t accumulate_edge, float* const* h_packed_grads, void* ws, int64_t ws_bytes,
                                  cgvp_stream_t stream) {
+    return cgvp_conv_bwd_stash(desc, plan, x_s, x_v, e_s, e_v, h_packed, d_out_s, d_out_v, d_x_s, d_x_v, d_e_s, d_e_v,
+                               accumulate_edge, h_packed_grads, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" int32_t cgvp_conv_bwd_stash(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
+                                       const float* e_s, const float* e_v, const float* const* h_packed, const float* d_out_s,
+                                       const float* d_out_v, float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v,
+                                       int32_t accumulate_edge, float* const* h_packed_grads, void* ws, int64_t ws_bytes,
+                                       const void* stash, cgvp_stream_t stream) {
     ConvK K;
     if (build_conv_k(desc, true, K)) return -1;
     if (conv_common_checks(K, plan, x_s, x_v, e_s, e_v, h_packed)) return -1;
@@ -540,7 +562,7 @@ extern "C" int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan,
             int rc = 0, grid = 0;
             if (conv_bwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, d_out_s, d_out_v, d_x_s, d_x_v, d_e_s, d_e_v,
                                  accumulate_edge, reinterpret_cast<float*>(base + oh), reinterpret_cast<float*>(base + ot), dj,
-                                 partial, sms_, st, &grid, &rc)) {
+                                 partial, sms_, reinterpret_cast<const float*>(stash), st, &grid, &rc)) {
                 if (rc) return rc;
                 rc = cgvp_segment_reduce_split(dj, K.ns + 3 * K.nv, plan->srowptr, plan->sperm, N, CGVP_AGGR_SUM, 1, d_x_s,
                                                K.ns, d_x_v, 3 * K.nv, st);

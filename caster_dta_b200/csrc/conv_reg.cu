@@ -25,6 +25,7 @@ struct ConvRegArgs {
     const float *d_out_s, *d_out_v;
     float *d_e_s, *d_e_v, *dj;
     float* partial;                       // [gridDim.x][PF] weight-gradient partials
+    float* stash;                         // [E][STASH] outputs of message GVPs 0 and 1 per sorted edge (forward writes, backward reads) or NULL
 };
 
 template <int NS_, int NV_, int ES_, int EV_, class G0_, class G1_, class G2_>
@@ -37,6 +38,7 @@ struct ConvSpec {
     static constexpr int SO = G2::SO, VO = G2::VO;
     static constexpr int CH = SO + 3 * VO;        // message channels = output node row
     static constexpr int CHX = NS + 3 * NV;       // node row (gradient slices)
+    static constexpr int ST1 = G0::SO + 3 * G0::VO, ST2 = G1::SO + 3 * G1::VO, STASH = ST1 + ST2;   // stage-input stash row
     // shared-memory weight offsets (floats)
     static constexpr int WF0 = 0, WF1 = G0::FWD_FLOATS, WF2 = WF1 + G1::FWD_FLOATS, WF = WF2 + G2::FWD_FLOATS;
     static constexpr int WT0 = 0, WT1 = G0::TOTAL_FLOATS, WT2 = WT1 + G1::TOTAL_FLOATS, WT = WT2 + G2::TOTAL_FLOATS;
@@ -98,6 +100,13 @@ __global__ void __launch_bounds__(CR_THREADS, 2) conv_fwd_reg_kernel(const __gri
         }
         float s2[1][G1::SO], v2[3][G1::VO1];
         { Save<G1> sv; gvp_fwd<G1>(wsm + S::WF1, s1, v1, s2, v2, sv); }
+        if (a.stash && lane < rv) {                             // training: the backward reads these instead of recomputing them
+            float* row = a.stash + p * S::STASH;
+            store_s<G0::SO, 0>(row, 0, s1, false);
+            store_v<G0::VO, 0>(row + G0::SO, 0, v1, false);
+            store_s<G1::SO, 0>(row + S::ST1, 0, s2, false);
+            store_v<G1::VO, 0>(row + S::ST1 + G1::SO, 0, v2, false);
+        }
         float s3[1][G2::SO], v3[3][G2::VO1];
         { Save<G2> sv; gvp_fwd<G2>(wsm + S::WF2, s2, v2, s3, v3, sv); }
 #pragma unroll
@@ -163,13 +172,21 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __gri
         WarpSink sink{reinterpret_cast<float4*>(stgf), arena, lane, valid};
         // forward chain, keeping only the stage inputs (each GVP is recomputed right before its backward)
         float s1[1][G0::SO], v1[3][G0::VO1], s2[1][G1::SO], v2[3][G1::VO1];
-        {
-            float s0[1][G0::SI], v0[3][G0::VI1];
-            load_message_input<S>(a, src, dst, eid, s0, v0);
-            Save<G0> sv;
-            gvp_fwd<G0>(wsm + S::WT0, s0, v0, s1, v1, sv);
+        if (a.stash) {                                            // written by the forward pass of the same call pair
+            const float* row = a.stash + p * S::STASH;
+            load_s<G0::SO, 0>(row, 0, s1);
+            load_v<G0::VO, 0>(row + G0::SO, 0, v1);
+            load_s<G1::SO, 0>(row + S::ST1, 0, s2);
+            load_v<G1::VO, 0>(row + S::ST1 + G1::SO, 0, v2);
+        } else {
+            {
+                float s0[1][G0::SI], v0[3][G0::VI1];
+                load_message_input<S>(a, src, dst, eid, s0, v0);
+                Save<G0> sv;
+                gvp_fwd<G0>(wsm + S::WT0, s0, v0, s1, v1, sv);
+            }
+            { Save<G1> sv; gvp_fwd<G1>(wsm + S::WT1, s1, v1, s2, v2, sv); }
         }
-        { Save<G1> sv; gvp_fwd<G1>(wsm + S::WT1, s1, v1, s2, v2, sv); }
         // d(message_e) = d_out[dst_e] (/ deg for mean)
         float gs3[1][S::SO], gv3[3][G2::VO1];
         load_s<S::SO, 0>(a.d_out_s, dst, gs3);
@@ -283,15 +300,18 @@ static void fill_common(ConvRegArgs& a, const CgvpConvDesc* desc, const CgvpPlan
 }
 
 // Returns 1 if this descriptor / these buffers are served by a specialised kernel (rc_out holds the result), else 0.
+int64_t conv_special_stash_floats(const CgvpConvDesc* desc) { return (g_fast_paths && ConvCk::matches(*desc)) ? ConvCk::STASH : 0; }
+
 int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, float* out_s, float* out_v, float* part_head,
-                     float* part_tail, cudaStream_t st, int* rc_out) {
+                     float* part_tail, float* stash, cudaStream_t st, int* rc_out) {
     using S = ConvCk;
     if (!g_fast_paths || !S::matches(*desc) || plan->num_edges <= 0 || plan->num_nodes <= 0) return 0;
     if (!(aligned16(x_s) && aligned16(x_v) && aligned16(e_s) && aligned16(out_s) && aligned16(out_v))) return 0;
     ConvRegArgs a;
     fill_common<S>(a, desc, plan, x_s, x_v, e_s, e_v, h_packed);
     a.out_s = out_s; a.out_v = out_v; a.part_head = part_head; a.part_tail = part_tail;
+    a.stash = (stash && aligned16(stash)) ? stash : nullptr;
     *rc_out = 0;
     const int sms = cgvp_num_sms();
     const int grid = (int)min((long long)cdiv(a.ntiles, CR_WARPS), (long long)sms * 2);
@@ -315,7 +335,8 @@ int conv_bwd_special_partial_floats(const CgvpConvDesc* desc) { return ConvCk::m
 int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, const float* d_out_s, const float* d_out_v,
                      float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
-                     float* part_tail, float* dj, float* partial, int max_grid, cudaStream_t st, int* grid_out, int* rc_out) {
+                     float* part_tail, float* dj, float* partial, int max_grid, const float* stash, cudaStream_t st, int* grid_out,
+                     int* rc_out) {
     using S = ConvCk;
     if (!g_fast_paths || !S::matches(*desc) || plan->num_edges <= 0 || plan->num_nodes <= 0) return 0;
     if (!(aligned16(x_s) && aligned16(x_v) && aligned16(e_s) && aligned16(d_out_s) && aligned16(d_out_v) && aligned16(d_x_s) &&
@@ -326,6 +347,7 @@ int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float
     a.out_s = d_x_s; a.out_v = d_x_v; a.part_head = part_head; a.part_tail = part_tail;
     a.d_out_s = d_out_s; a.d_out_v = d_out_v; a.d_e_s = d_e_s; a.d_e_v = d_e_v; a.dj = dj; a.acc_edge = accumulate_edge;
     a.partial = partial;
+    a.stash = (stash && aligned16(stash)) ? const_cast<float*>(stash) : nullptr;
     *rc_out = 0;
     const int sms = cgvp_num_sms();
     int grid = (int)min((long long)cdiv(a.ntiles, CR_WARPS), (long long)sms);

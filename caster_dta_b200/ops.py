@@ -296,6 +296,9 @@ class ConvProgram:
         self.desc = d
 
 
+USE_CONV_STASH = True    # forward stash for the conv backward (cgvp_conv_fwd_stash / cgvp_conv_bwd_stash)
+
+
 class ConvFunction(torch.autograd.Function):
     """autograd wrapper of cgvp_conv_fwd / cgvp_conv_bwd."""
 
@@ -310,8 +313,15 @@ class ConvFunction(torch.autograd.Function):
         nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 0)
         ws = _workspace(nbytes, dev)
         wp, wn = _aligned_ptr(ws)
-        _lib.timed_call("cgvp_conv_fwd", lib().cgvp_conv_fwd, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
-                                  _ptr(out_s), _ptr(out_v), wp, wn, _stream())
+        # training: the specialised kernels leave the inputs of message GVPs 1 and 2 per edge for the backward (USE_CONV_STASH)
+        stash = None
+        if USE_CONV_STASH and any(ctx.needs_input_grad):
+            sbytes = lib().cgvp_conv_stash_bytes(C.byref(prog.desc), plan.E)
+            if sbytes > 0:
+                stash = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+        _lib.timed_call("cgvp_conv_fwd", lib().cgvp_conv_fwd_stash, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s),
+                        _ptr(e_v), blocks, _ptr(out_s), _ptr(out_v), wp, wn, _ptr(stash), _stream())
+        ctx.stash = stash
         ctx.prog, ctx.plan, ctx.saved, ctx.arena, ctx.offs, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), arena, offs, weights
         ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
         return out_s, out_v
@@ -331,9 +341,9 @@ class ConvFunction(torch.autograd.Function):
         nbytes = lib().cgvp_conv_workspace_bytes(C.byref(prog.desc), plan.E, plan.N, 1)
         ws = _workspace(nbytes, dev)
         wp, wn = _aligned_ptr(ws)
-        _lib.timed_call("cgvp_conv_bwd", lib().cgvp_conv_bwd, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s), _ptr(e_v), blocks,
-                                  _ptr(d_out_s), _ptr(d_out_v), _ptr(d_x_s), _ptr(d_x_v), _ptr(d_e_s), _ptr(d_e_v), 0,
-                                  gblocks, wp, wn, _stream())
+        _lib.timed_call("cgvp_conv_bwd", lib().cgvp_conv_bwd_stash, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s),
+                        _ptr(e_v), blocks, _ptr(d_out_s), _ptr(d_out_v), _ptr(d_x_s), _ptr(d_x_v), _ptr(d_e_s), _ptr(d_e_v), 0,
+                        gblocks, wp, wn, _ptr(ctx.stash), _stream())
         dw = unpack_grads(prog.gvps, pg, ctx.offs, ctx.weights)
         return (None, None, d_x_s, d_x_v, d_e_s, d_e_v, *dw)
 

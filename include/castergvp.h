@@ -149,6 +149,19 @@ int32_t cgvp_conv_bwd(const CgvpConvDesc* desc, const CgvpPlan* plan, const floa
                       const float* d_out_v, float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v,
                       int32_t accumulate_edge, float* const* h_packed_grads, void* ws, int64_t ws_bytes,
                       cgvp_stream_t stream);
+/* Optional training stash: the forward of the specialised kernels can leave the outputs of message GVPs 0 and 1 per
+ * (sorted) edge in a caller-owned buffer of cgvp_conv_stash_bytes() bytes, and the backward of the SAME call pair reads them
+ * instead of recomputing the first two GVPs (-21 % FMAs in the backward for 224 B/edge of extra traffic).  0 bytes = the
+ * descriptor has no such path; stash = NULL reproduces cgvp_conv_fwd / cgvp_conv_bwd. */
+int64_t cgvp_conv_stash_bytes(const CgvpConvDesc* desc, int64_t num_edges);
+int32_t cgvp_conv_fwd_stash(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
+                            const float* e_s, const float* e_v, const float* const* h_packed, float* out_s, float* out_v,
+                            void* ws, int64_t ws_bytes, void* stash, cgvp_stream_t stream);
+int32_t cgvp_conv_bwd_stash(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v,
+                            const float* e_s, const float* e_v, const float* const* h_packed, const float* d_out_s,
+                            const float* d_out_v, float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v,
+                            int32_t accumulate_edge, float* const* h_packed_grads, void* ws, int64_t ws_bytes,
+                            const void* stash, cgvp_stream_t stream);
 
 /* ---- fused row program ---------------------------------------------------------------------------------------
  * One kernel for every per-row (per-node or per-edge) stage of the path:
