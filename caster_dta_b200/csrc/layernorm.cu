@@ -112,14 +112,26 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     }
 }
 
-__global__ void ln_reduce_kernel(const float* __restrict__ partial, int parts, int D, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * D) return;
-    float s0 = 0.f, s1 = 0.f;
-    int p = 0;
-    for (; p + 1 < parts; p += 2) { s0 += partial[(long long)p * 2 * D + i]; s1 += partial[(long long)(p + 1) * 2 * D + i]; }
-    if (p < parts) s0 += partial[(long long)p * 2 * D + i];
-    (i < D ? dgamma[i] : dbeta[i - D]) = s0 + s1;
+// dgamma / dbeta = sum of the per-CTA partials.  Block = 8 warps x 32 columns: warp w sums partials w, w + 8, ... of its
+// lane's column (coalesced, 8 loads in flight), the eight slices meet in shared memory in warp order: deterministic.
+__global__ void __launch_bounds__(256) ln_reduce_kernel(const float* __restrict__ partial, int parts, int D, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta) {
+    __shared__ float sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                       // column of the [parts][2D] partial matrix
+    float s = 0.f;
+    if (i < 2 * D) {
+#pragma unroll 8
+        for (int p = w; p < parts; p += 8) s += __ldg(partial + (long long)p * 2 * D + i);
+    }
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < 2 * D) {
+        float t = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) t += sm[ww][lane];
+        (i < D ? dgamma[i] : dbeta[i - D]) = t;
+    }
 }
 
 static int ln_grid(int64_t rows) {
@@ -166,7 +178,7 @@ extern "C" int32_t cgvp_layernorm_bwd(const float* dy, const float* x, const flo
     else if (D == 128) ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dy, x, stats, gamma, rows, dx, partial);
     else ln_bwd_kernel<8><<<grid, 256, 0, st>>>(dy, x, stats, gamma, rows, dx, partial);
     CGVP_LAUNCH_CHECK("ln_bwd_kernel");
-    ln_reduce_kernel<<<cdiv(2 * D, 128), 128, 0, st>>>(partial, grid, D, dgamma, dbeta);
+    ln_reduce_kernel<<<cdiv(2 * D, 32), 256, 0, st>>>(partial, grid, D, dgamma, dbeta);
     CGVP_LAUNCH_CHECK("ln_reduce_kernel");
     return 0;
 }

@@ -160,25 +160,30 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     if (warp == 0) tcx::tmem_dealloc(tm0, tmem_cols);
 }
 
-// fixed-order sum of the S partials (four interleaved chains, combined at the end: always the same association)
-__device__ __forceinline__ float wg_sum_partials(const float* __restrict__ p, long long stride, int S) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int q = 0;
-#pragma unroll 2
-    for (; q + 3 < S; q += 4) {
-        s0 += __ldg(p + (long long)q * stride);
-        s1 += __ldg(p + (long long)(q + 1) * stride);
-        s2 += __ldg(p + (long long)(q + 2) * stride);
-        s3 += __ldg(p + (long long)(q + 3) * stride);
+// Sum of the S partials.  Block = 8 warps x 32 outputs: warp w sums partials w, w + 8, ... of its lane's output (coalesced,
+// several loads in flight), the eight slices meet in shared memory in warp order: the association is fixed -> deterministic.
+__global__ void __launch_bounds__(256) lin_wgrad_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb, int S,
+                                                                long long nk, int N, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + lane;      // output index: [0, nk) = dW, [nk, nk + N) = db
+    const bool is_w = i < nk, is_b = !is_w && db && i < nk + N;
+    float s = 0.f;
+    if (is_w) {
+#pragma unroll 6
+        for (int p = w; p < S; p += 8) s += __ldg(pw + (long long)p * nk + i);
+    } else if (is_b) {
+#pragma unroll 6
+        for (int p = w; p < S; p += 8) s += __ldg(pb + (long long)p * N + (i - nk));
     }
-    for (; q < S; ++q) s0 += __ldg(p + (long long)q * stride);
-    return (s0 + s1) + (s2 + s3);
-}
-__global__ void lin_wgrad_reduce_kernel(const float* __restrict__ pw, const float* __restrict__ pb, int S, long long nk, int N,
-                                        float* __restrict__ dw, float* __restrict__ db) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nk) dw[i] = wg_sum_partials(pw + i, nk, S);
-    else if (db && i < nk + N) db[i - nk] = wg_sum_partials(pb + (i - nk), N, S);
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && (is_w || is_b)) {
+        float t = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) t += sm[ww][lane];
+        if (is_w) dw[i] = t; else db[i - nk] = t;
+    }
 }
 
 static void wgrad_plan(int64_t M, int32_t N, int* S, long long* rows_per_cta) {
@@ -230,7 +235,7 @@ extern "C" int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M,
     lin_wgrad_kernel<<<dim3((unsigned)S, (unsigned)(N / 128)), 128, smem, st>>>(a);
     CGVP_LAUNCH_CHECK("lin_wgrad_kernel");
     const long long nk = (long long)N * K;
-    lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 128), 128, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
+    lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 32), 256, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
     CGVP_LAUNCH_CHECK("lin_wgrad_reduce_kernel");
     return 0;
 }
