@@ -233,12 +233,25 @@ extern "C" int32_t cgvp_unpack_grads(int32_t n, const CgvpGvpDesc* h_descs, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nparts, int stride, int n, float* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// out[i] = sum over the CTA partials.  Block = 8 warps x 32 outputs: warp w sums partials w, w + 8, ... of its lane's output
+// (coalesced, several loads in flight); the eight slices are combined in warp order -- a fixed association, deterministic.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int stride, int n, float* out) {
+    __shared__ float sm[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int c = 0; c < nparts; ++c) s += partial[(long long)c * stride + i];
-    out[i] = s;
+    if (i < n) {
+#pragma unroll 6
+        for (int c = w; c < nparts; c += 8) s += __ldg(partial + (long long)c * stride + i);
+    }
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) t += sm[ww][lane];
+        out[i] = t;
+    }
 }
 
 struct SegPack { CgvpSeg s[CGVP_MAX_SEGS]; };
@@ -252,7 +265,7 @@ int cgvp_reduce_partials(const float* partial, int nparts, int stride, float* re
                          cudaStream_t stream) {
     if (stride <= 0) return 0;
     CGVP_REQUIRE(nsegs <= CGVP_MAX_SEGS, "too many gradient segments");
-    reduce_partials_kernel<<<cdiv(stride, 256), 256, 0, stream>>>(partial, nparts, stride, stride, reduced);
+    reduce_partials_kernel<<<cdiv(stride, 32), 256, 0, stream>>>(partial, nparts, stride, stride, reduced);
     CGVP_LAUNCH_CHECK("reduce_partials_kernel");
     if (nsegs > 0) {
         SegPack sp;
