@@ -467,6 +467,10 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(traffic_file):
         roof["traffic"] = json.load(open(traffic_file)).get(dominant)
+        if dominant == "conv_bwd":
+            roof["traffic_note"] = ("DRAM bytes include reading the 224 B/edge training stash written by the forward (a deliberate "
+                                    "recompute-for-traffic trade, cgvp_conv_fwd_stash) and the dj round trip; algorithmic bytes are the "
+                                    "compulsory traffic without it")
 
     # ---- CPU baseline (bounded sample) --------------------------------------------------------------------------------------
     cpu = None
