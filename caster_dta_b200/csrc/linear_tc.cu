@@ -15,6 +15,8 @@
 #include "cgvp_tc.cuh"
 
 #define WG_RB 32                          // rows (reduction steps) per stage = 4 MMA k-blocks; sets the bytes in flight per CTA
+#define WG_NT 512                         // threads per CTA: 16 warps share the split / store work of a stage
+#define WG_NW (WG_NT / 32)
 #define WG_GROUP_BYTES (WG_RB * 128)      // one 32-column group of a stage: [4-step atom][4 steps][128 B]
 
 struct WgradArgs {
@@ -37,15 +39,15 @@ __device__ __forceinline__ void wg_split_store(unsigned char* hi, unsigned char*
     *reinterpret_cast<float4*>(lo + off) = l;
 }
 
-__global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+__global__ void __launch_bounds__(WG_NT) lin_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = a.K, KG = K / 32, KC = K / 4;                  // column groups / 16-byte chunks per X row
     // two stage buffers, each [A_hi | A_lo | B_hi | B_lo]
     const int stage_bytes = 2 * 4 * WG_GROUP_BYTES + 2 * KG * WG_GROUP_BYTES;
-    float* bsm = reinterpret_cast<float*>(smem + 2 * stage_bytes);             // [4 warps][128] bias staging
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(bsm + 4 * 128);                // [2] one per buffer
+    float* bsm = reinterpret_cast<float*>(smem + 2 * stage_bytes);             // [WG_NW warps][128] bias staging
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(bsm + WG_NW * 128);            // [2] one per buffer
     uint32_t* slot = reinterpret_cast<uint32_t*>(mbar + 2);
     const int tmem_cols = K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256));
     if (tid == 0) { tcx::mbar_init(mbar, 1); tcx::mbar_init(mbar + 1, 1); tcx::fence_mbar_init(); }
@@ -63,23 +65,26 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     const float4* x4 = reinterpret_cast<const float4*>(a.x);
     const long long dy_ld4 = a.N / 4;
     const int c_a = tid & 31;                                    // this thread's dY chunk column (fixed) ...
-    const int r_a = tid >> 5;                                    // ... rows r_a, r_a + 4, ... of a stage
-    const int nb = (WG_RB * KC) / 128;                           // X chunks per thread per stage (KC % 8 == 0 -> exact)
-    float4 ra[WG_RB / 4], rb[WG_RB / 2];
+    const int r_a = tid >> 5;                                    // ... rows r_a, r_a + WG_NW, ... of a stage
+    constexpr int NA = WG_RB / WG_NW;                            // dY chunks per thread per stage
+    constexpr int NBMAX = (WG_RB * 64) / WG_NT;                  // X chunks per thread per stage at K = 256
+    const int nchunk_b = WG_RB * KC, nb = (nchunk_b + WG_NT - 1) / WG_NT;
+    float4 ra[NA], rb[NBMAX];
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto load_stage = [&](int st) {
         const long long r0 = row_begin + (long long)st * WG_RB;
 #pragma unroll
-        for (int i = 0; i < WG_RB / 4; ++i) {
-            const long long r = r0 + r_a + 4 * i;
+        for (int i = 0; i < NA; ++i) {
+            const long long r = r0 + r_a + WG_NW * i;
             ra[i] = r < row_end ? __ldg(dy4 + r * dy_ld4 + mt * 32 + c_a) : zero4;
         }
 #pragma unroll
-        for (int i = 0; i < WG_RB / 2; ++i) {
-            if (i < nb) {
-                const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
+        for (int i = 0; i < NBMAX; ++i) {
+            const int q = tid + WG_NT * i;
+            if (i < nb && q < nchunk_b) {
+                const int r = q / KC, c = q - r * KC;
                 const long long rr = r0 + r;
                 rb[i] = rr < row_end ? __ldg(x4 + rr * KC + c) : zero4;
             }
@@ -96,14 +101,15 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
         unsigned char* B_lo = B_hi + KG * WG_GROUP_BYTES;
         if (st >= 2) { tcx::mbar_wait(mbar + buf, phase[buf]); phase[buf] ^= 1; }   // the MMAs of stage st-2 have read this buffer
 #pragma unroll
-        for (int i = 0; i < WG_RB / 4; ++i) {
-            wg_split_store(A_hi, A_lo, wg_off(r_a + 4 * i, c_a), ra[i]);
+        for (int i = 0; i < NA; ++i) {
+            wg_split_store(A_hi, A_lo, wg_off(r_a + WG_NW * i, c_a), ra[i]);
             bsum.x += ra[i].x; bsum.y += ra[i].y; bsum.z += ra[i].z; bsum.w += ra[i].w;
         }
 #pragma unroll
-        for (int i = 0; i < WG_RB / 2; ++i) {
-            if (i < nb) {
-                const int q = tid + 128 * i, r = q / KC, c = q - r * KC;
+        for (int i = 0; i < NBMAX; ++i) {
+            const int q = tid + WG_NT * i;
+            if (i < nb && q < nchunk_b) {
+                const int r = q / KC, c = q - r * KC;
                 wg_split_store(B_hi, B_lo, wg_off(r, c), rb[i]);
             }
         }
@@ -132,11 +138,12 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
     if (nstages > 0) { const int b = (nstages - 1) & 1; tcx::mbar_wait(mbar + b, phase[b]); phase[b] ^= 1; }
     if (nstages > 1) { const int b = (nstages - 2) & 1; tcx::mbar_wait(mbar + b, phase[b]); phase[b] ^= 1; }
     tcx::tc_fence_after();
-    // partial dW tile: TMEM lane = dW row
+    // partial dW tile: TMEM lane = dW row; warp w reads lanes 32 (w % 4) .. +31 and the column slices w / 4, w / 4 + 4, ...
     {
-        const uint32_t tm = tm0 + ((uint32_t)(warp * 32) << 16);
-        float* out = a.pw + ((long long)split * a.N + mt * 128 + warp * 32 + lane) * K;
-        for (int c0 = 0; c0 < K; c0 += 16) {
+        const int lg = warp & 3;
+        const uint32_t tm = tm0 + ((uint32_t)(lg * 32) << 16);
+        float* out = a.pw + ((long long)split * a.N + mt * 128 + lg * 32 + lane) * K;
+        for (int c0 = (warp >> 2) * 16; c0 < K; c0 += (WG_NW / 4) * 16) {
             float d[16];
             if (nstages > 0) {
                 tcx::tmem_ld16(tm + c0, d);
@@ -149,13 +156,15 @@ __global__ void __launch_bounds__(128) lin_wgrad_kernel(const __grid_constant__ 
             for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(out + c0)[j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
         }
     }
-    // partial db: the four warps hold disjoint rows of the same 32 column chunks
+    // partial db: the warps hold disjoint rows of the same 32 column chunks
     reinterpret_cast<float4*>(bsm + warp * 128)[lane] = bsum;
     tcx::tc_fence_before();
     __syncthreads();
     if (a.pb && tid < 128) {
-        const float s = bsm[tid] + bsm[128 + tid] + bsm[256 + tid] + bsm[384 + tid];
-        a.pb[(long long)split * a.N + mt * 128 + tid] = s;
+        float sb = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < WG_NW; ++w2) sb += bsm[w2 * 128 + tid];
+        a.pb[(long long)split * a.N + mt * 128 + tid] = sb;
     }
     if (warp == 0) tcx::tmem_dealloc(tm0, tmem_cols);
 }
@@ -230,9 +239,9 @@ extern "C" int32_t cgvp_linear_wgrad(const float* dy, const float* x, int64_t M,
     a.pw = reinterpret_cast<float*>(b);
     a.pb = reinterpret_cast<float*>(b + align_up((int64_t)S * N * K * 4, 256));
     const int KG = K / 32;
-    const size_t smem = 1024 + 2 * (2 * 4 * WG_GROUP_BYTES + 2 * (size_t)KG * WG_GROUP_BYTES) + 4 * 128 * 4 + 64;
+    const size_t smem = 1024 + 2 * (2 * 4 * WG_GROUP_BYTES + 2 * (size_t)KG * WG_GROUP_BYTES) + WG_NW * 128 * 4 + 64;
     CGVP_CUDA(cudaFuncSetAttribute(lin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lin_wgrad_kernel<<<dim3((unsigned)S, (unsigned)(N / 128)), 128, smem, st>>>(a);
+    lin_wgrad_kernel<<<dim3((unsigned)S, (unsigned)(N / 128)), WG_NT, smem, st>>>(a);
     CGVP_LAUNCH_CHECK("lin_wgrad_kernel");
     const long long nk = (long long)N * K;
     lin_wgrad_reduce_kernel<<<(unsigned)cdiv64(nk + N, 32), 256, 0, st>>>(a.pw, a.pb, S, nk, N, dw, db);
