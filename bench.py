@@ -275,6 +275,7 @@ def main():
     kw = caster_dta_2_2()
     torch.manual_seed(9)
     model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"]).to(dev).train()
+    model.overlap_encoders = os.environ.get("CGVP_OVERLAP", "1") == "1"
     parallel.broadcast_parameters(model, 0)
     bucket = parallel.GradSync(model)
     opt = torch.optim.Adam(bucket.params, lr=1e-4, fused=True, capturable=True)

@@ -312,6 +312,8 @@ class JointGNN(nn.Module):
         self.num_cross_attn_layers = num_cross_attn_layers
         self.include_post_pool_layernorm = include_post_pool_layernorm
         self.return_attention = True
+        self.overlap_encoders = False        # run the molecule encoder on a side stream (set by the training driver)
+        self._side_stream = None
         self.activation = _activation(activation)
         self.dropout = nn.Dropout(dropout)
         self.protein_gnn = SelectableProteinModelWrapper(**protein_gnn_kwargs)
@@ -367,12 +369,31 @@ class JointGNN(nn.Module):
         # `protein_embed`: residue embeddings computed earlier for the same protein(s) -- the encoder
         # output depends on the protein only, so an inference sweep over many ligands per protein can reuse it
         embed = pg.pop("protein_embed", None)
+        # The two encoders are independent (`models/joint_gnn.py:183-190`): the molecule side -- ~60 tiny kernels on ~10^3
+        # atoms -- runs on a side stream under the protein encoder's large kernels (fork / join, also inside graph capture;
+        # autograd replays each side's backward on the stream of its forward).
+        side = None
+        x_mol = mg.get("x")
+        if self.overlap_encoders and torch.is_tensor(x_mol) and x_mol.is_cuda:
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=x_mol.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
+                dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
         if embed is None:
             embed = self.protein_gnn(**pg)
         res = self._stack(embed, self.residue_lins, self.residue_norms)
-        atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
         dp = DenseIndex(pg.get("batch"), res.shape[0], device=res.device, **hints_p)
-        dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
+        if side is None:
+            atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
+            dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
+        else:
+            torch.cuda.current_stream().wait_stream(side)
+            for t in (atm, dm.idx, dm.mask, dm.batch, dm.ptr):
+                t.record_stream(torch.cuda.current_stream())
         weights = None
         if self.cross_attn_module is not None:
             res, atm, weights = self.cross_attn_module.forward_packed(res, atm, dp, dm, self.return_attention)

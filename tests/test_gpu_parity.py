@@ -200,6 +200,24 @@ def test_joint_small_golden():
     assert_close(emb, out["residue_embed"], TIGHT, "residue embedding")
     assert_close(pred, out["pred"], TOL, "affinity")
     assert_close(weights[0][0], out["attn_p2m"], TOL, "attention")
+    # molecule encoder on a side stream (the training driver's setting): same results, forward and gradients, up to the
+    # run-to-run noise of the stock GINE stand-in (its index_add_ uses atomics)
+    def run(overlap):
+        model.overlap_encoders = overlap
+        model.zero_grad(set_to_none=True)
+        p, w = model(prot, mol)
+        p.square().sum().backward()
+        torch.cuda.synchronize()
+        return p.detach().clone(), w[0][0].detach().clone(), [q.grad.clone() for q in model.parameters() if q.grad is not None]
+    a, b = run(False), run(True)
+    c = run(False)
+    noise = max(float((a[0] - c[0]).abs().max()), 1e-7)
+    assert float((a[0] - b[0]).abs().max()) <= 20 * noise + 1e-6 * float(a[0].abs().max())
+    assert_close(b[1], a[1], 1e-5, "attention map with the side stream")
+    assert len(a[2]) == len(b[2])
+    for x, y in zip(a[2], b[2]):
+        assert_close(y, x, 1e-4, "gradient with the side stream", atol=1e-6)
+    model.overlap_encoders = False
 
 
 FEAT_SETTINGS = ["dist4_self", "dist8_noself", "num10_self", "num8_noself", "prop_self", "num_gt_n"]
