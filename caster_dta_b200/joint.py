@@ -228,6 +228,7 @@ class CrossAttentionModule(nn.Module):
                                                  vdim=embed_dim_1, batch_first=True)
         self.ff_norm1, self.ff_norm2 = nn.LayerNorm(embed_dim_1), nn.LayerNorm(embed_dim_2)
         self.ff_dropout = nn.Dropout(feedforward_dropout)
+        self.side_stream = None              # set by JointGNN when overlap_encoders is on
         if include_residual_stream:
             def ff(d):
                 return nn.Sequential(nn.Linear(d, d * dim_feedforward_scale), nn.ReLU(), nn.Dropout(feedforward_dropout),
@@ -252,16 +253,34 @@ class CrossAttentionModule(nn.Module):
         n1, n2 = ops.layer_norm(x1, self.preattn_norm1), ops.layer_norm(x2, self.preattn_norm2)
         f1 = self.preattn_norm1.bias if first else None
         f2 = self.preattn_norm2.bias if first else None
+
+        def stream2():                       # everything that only feeds the second stream's output (atoms: many tiny kernels)
+            a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
+            if not self.include_residual_stream:
+                return a2, w2
+            y2 = x2 + self.ff_dropout(a2)
+            return y2 + self.ff_dropout(_seq(self.ff2, ops.layer_norm(y2, self.ff_norm2))), w2
+
+        side = self.side_stream if x1.is_cuda else None
+        if side is not None:                 # the two directions are independent: run the second on the side stream
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                y2, w2 = stream2()
         a1, w1 = _mha_packed(self.embed1_to_2, n1, n2, d1, d2, f1, return_weights, self.training)
-        a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
         if self.include_residual_stream:
             x1 = x1 + self.ff_dropout(a1)
             x1 = x1 + self.ff_dropout(_seq(self.ff1, ops.layer_norm(x1, self.ff_norm1)))
-            x2 = x2 + self.ff_dropout(a2)
-            x2 = x2 + self.ff_dropout(_seq(self.ff2, ops.layer_norm(x2, self.ff_norm2)))
         else:
-            x1, x2 = a1, a2
-        return x1, x2, (w1, w2)
+            x1 = a1
+        if side is not None:
+            main.wait_stream(side)
+            for t in (y2, w2):
+                if t is not None:
+                    t.record_stream(main)
+        else:
+            y2, w2 = stream2()
+        return x1, y2, (w1, w2)
 
 
 class StackedCrossAttentionModule(nn.Module):
@@ -396,6 +415,8 @@ class JointGNN(nn.Module):
                 t.record_stream(torch.cuda.current_stream())
         weights = None
         if self.cross_attn_module is not None:
+            for layer in self.cross_attn_module.cross_attn_layers:
+                layer.side_stream = side
             res, atm, weights = self.cross_attn_module.forward_packed(res, atm, dp, dm, self.return_attention)
         pe, me = self._pool(dp.pad(res), dp.mask), self._pool(dm.pad(atm), dm.mask)
         if self.include_post_pool_layernorm:
