@@ -458,13 +458,14 @@ def main():
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_launch"] = alg_bytes
         # context: at checkpoint dims this kernel is fp32-FMA bound (31 FLOP/B > the 11 FLOP/B CUDA-core ridge), so also report
-        # the arithmetic side -- algorithmic FLOPs (5 086 / edge forward, x4 for the backward with recompute) against the FFMA peak
-        flops = 5086.0 * e * (4.0 if dominant == "conv_bwd" else 1.0)
+        # the arithmetic side -- ALGORITHMIC FLOPs (5 086 / edge forward; the backward is 2x that, SURVEY 8d -- the forward
+        # recompute the kernel also does is not counted) against the FFMA peak
+        flops = 5086.0 * e * (2.0 if dominant == "conv_bwd" else 1.0)
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = sm_count * 128 * 2 * (clock_info or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         roof["fp32"] = {"achieved_tflops": flops / (kms / kn * 1e-3) / 1e12, "peak_tflops": fp32_peak,
                         "frac": flops / (kms / kn * 1e-3) / 1e12 / fp32_peak,
-                        "note": "FFMA peak = SMs x 128 lanes x 2 x max SM clock; the HBM fraction above is small because the kernel is arithmetic bound"}
+                        "note": "algorithmic FLOPs (recompute not counted) against FFMA peak = SMs x 128 lanes x 2 x max SM clock; the kernel is arithmetic / issue bound, which is why its HBM fraction is small"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(traffic_file):
         roof["traffic"] = json.load(open(traffic_file)).get(dominant)
