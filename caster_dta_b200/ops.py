@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and autograd bookkeeping only; all ar
 happens in `libcastergvp.so`.  Every call is enqueued on the current CUDA stream.
 """
 import ctypes as C
+import functools
 import weakref
 
 import torch
@@ -380,6 +381,7 @@ def segment_reduce(rows, plan, aggr="sum", use_perm=True, out=None, beta=0):
 
 
 # ---- cross-attention core on packed rows (csrc/attention.cu) ---------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
 def attention_supported(num_heads, head_dim):
     return bool(lib().cgvp_attn_supported(int(num_heads), int(head_dim)))
 
@@ -446,6 +448,7 @@ def linear_wgrad(dy, x, want_bias=True):
     return dw, db
 
 
+@functools.lru_cache(maxsize=4096)
 def linear_wgrad_supported(m, n, k):
     return bool(lib().cgvp_linear_wgrad_supported(int(m), int(n), int(k)))
 
@@ -541,9 +544,14 @@ class LayerNormFunction(torch.autograd.Function):
         return dx, dg, db, None
 
 
+@functools.lru_cache(maxsize=None)
+def _layernorm_supported(d):
+    return bool(lib().cgvp_layernorm_supported(d))
+
+
 def layer_norm(x, mod):
     """`mod(x)` for an affine nn.LayerNorm over the last dimension of packed 2-D CUDA activations."""
     if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and mod.elementwise_affine and mod.bias is not None
-            and len(mod.normalized_shape) == 1 and x.shape[0] > 0 and lib().cgvp_layernorm_supported(int(x.shape[1]))):
+            and len(mod.normalized_shape) == 1 and x.shape[0] > 0 and _layernorm_supported(int(x.shape[1]))):
         return LayerNormFunction.apply(x, mod.weight, mod.bias, mod.eps)
     return mod(x)
