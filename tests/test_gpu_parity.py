@@ -506,6 +506,34 @@ def test_fast_and_generic_kernels_agree_in_training_mode():
         assert_close(f[5][k], gnr[5][k].cpu(), TIGHT, "grad " + k, atol=1e-5)
 
 
+def test_conv_training_stash_is_bit_identical_to_recompute():
+    """cgvp_conv_fwd_stash / cgvp_conv_bwd_stash (the backward reads the stage inputs the forward left) against the plain
+    entry points (the backward recomputes them): same arithmetic, so every output and gradient must be the same bits."""
+    cg = _mods()
+    from caster_dta_b200 import ops
+    import torch.nn.functional as F
+    nd, ed = (16, 4), (32, 1)
+    p, ei, x, ea = _random_layer_case(2111, 40007, nd, ed, seed=17, hub=True, aggr="mean")
+    m = cg.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean")
+    m.load_state_dict(p, strict=True)
+    m.to(DEV).train()
+    cot = torch.randn(2111, 16, generator=torch.Generator().manual_seed(1)).to(DEV)
+    res = {}
+    for stash in (True, False):
+        prev, ops.USE_CONV_STASH = ops.USE_CONV_STASH, stash
+        try:
+            xs, xv, es, ev = _leaf(x[0]), _leaf(x[1]), _leaf(ea[0]), _leaf(ea[1])
+            m.zero_grad(set_to_none=True)
+            out = m((xs, xv), ei.to(DEV), (es, ev))
+            (out[0] * cot).sum().backward()
+            res[stash] = [out[0].detach(), out[1].detach(), xs.grad, xv.grad, es.grad, ev.grad] + [q.grad.clone() for q in m.parameters() if q.numel()]
+        finally:
+            ops.USE_CONV_STASH = prev
+    assert len(res[True]) == len(res[False])
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("n,e,aggr,hub", [(900, 27000, "mean", False), (700, 9001, "sum", True), (200, 130, "sum", False)])
 def test_tensor_core_conv_forward_vs_oracle(n, e, aggr, hub):
     """tcgen05 path (bf16 operands, fp32 accumulation in TMEM) of the fused GVPConv forward at config-5 dims
