@@ -52,6 +52,7 @@ def main():
         pool.append(dict(coords=t(pb["coords"]), ptr=t(pb["ptr"]), x_s=t(pb["x_s"]), x_v=t(pb["x_v"]), nt=t(pb["ntypes"]),
                          batch=t(pb["batch"]), max_res=int(np.diff(pb["ptr"]).max()),
                          mol={k: t(v) for k, v in mol.items()}, max_atoms=int(np.bincount(mol["batch"]).max())))
+    aa_table = torch.rand(20, 11, generator=torch.Generator().manual_seed(5)).to(dev)      # synthetic residue property table
     my_batches = len(range(rank, args.pairs // args.batch, world))
     preds, edges, residues = [], 0, 0
 
@@ -65,8 +66,10 @@ def main():
                         batch=m["batch"], num_graphs=args.batch, max_nodes=d["max_atoms"])
             if embed is None or i % args.ligands_per_protein == 0:
                 dp = d                                   # the protein batch the next L ligand batches are paired with
-                ei, eattr, et = cg.residue_graph_batch(d["coords"], d["ptr"], thresh, ttype, True)
-                embed = model.protein_gnn(x=(d["x_s"], d["x_v"]), edge_index=ei, ntypes=d["nt"], etypes=et, eattr=eattr, batch=d["batch"])
+                # backbone coordinates -> node features -> residue graph -> encoder, all on the device
+                pgb = cg.protein_graph_batch(d["coords"], d["ptr"], d["nt"], aa_table, thresh, ttype, True)
+                ei = pgb["edge_index"]
+                embed = model.protein_gnn(**pgb)
                 if count:
                     edges += int(ei.shape[1]); residues += int(d["x_s"].shape[0])
             prot = dict(batch=dp["batch"], num_graphs=args.batch, max_nodes=dp["max_res"], protein_embed=embed)
@@ -96,7 +99,7 @@ def main():
                           "protein_graphs_built": int(cnt[2]), "protein_edges": int(cnt[1]),
                           "ligands_per_protein": args.ligands_per_protein,
                           "finite": bool(torch.isfinite(torch.cat(preds)).all()),
-                          "note": "featurizer + encoder + cross-attention + head per batch, inputs resident, no collective"}))
+                          "note": "node + edge featurizer from backbone coordinates, encoder, cross-attention, head per batch; coordinates resident, no collective"}))
     if world > 1:
         dist.destroy_process_group()
 
