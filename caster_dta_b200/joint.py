@@ -388,6 +388,7 @@ class JointGNN(nn.Module):
         # `protein_embed`: residue embeddings computed earlier for the same protein(s) -- the encoder
         # output depends on the protein only, so an inference sweep over many ligands per protein can reuse it
         embed = pg.pop("protein_embed", None)
+        dp_cached = pg.pop("dense_index", None)          # optional: the DenseIndex of the same protein batch (see protein_embed)
         # The two encoders are independent (`models/joint_gnn.py:183-190`): the molecule side -- ~60 tiny kernels on ~10^3
         # atoms -- runs on a side stream under the protein encoder's large kernels (fork / join, also inside graph capture;
         # autograd replays each side's backward on the stream of its forward).
@@ -405,7 +406,7 @@ class JointGNN(nn.Module):
         if embed is None:
             embed = self.protein_gnn(**pg)
         res = self._stack(embed, self.residue_lins, self.residue_norms)
-        dp = DenseIndex(pg.get("batch"), res.shape[0], device=res.device, **hints_p)
+        dp = dp_cached if dp_cached is not None else DenseIndex(pg.get("batch"), res.shape[0], device=res.device, **hints_p)
         if side is None:
             atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
             dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)

@@ -23,6 +23,7 @@ import torch.distributed as dist
 
 import caster_dta_b200 as cg
 from caster_dta_b200 import synth
+from caster_dta_b200 import joint
 from caster_dta_b200.configs import caster_dta_2_2
 
 
@@ -58,7 +59,7 @@ def main():
 
     def run(nb, count):
         nonlocal edges, residues
-        embed, dp = None, None
+        embed, dp, dense = None, None, None
         for i in range(nb):
             d = pool[i % len(pool)]
             m = d["mol"]
@@ -70,9 +71,12 @@ def main():
                 pgb = cg.protein_graph_batch(d["coords"], d["ptr"], d["nt"], aa_table, thresh, ttype, True)
                 ei = pgb["edge_index"]
                 embed = model.protein_gnn(**pgb)
+                dense = None
                 if count:
                     edges += int(ei.shape[1]); residues += int(d["x_s"].shape[0])
-            prot = dict(batch=dp["batch"], num_graphs=args.batch, max_nodes=dp["max_res"], protein_embed=embed)
+            if dense is None:
+                dense = joint.DenseIndex(dp["batch"], int(dp["batch"].shape[0]), num_graphs=args.batch, max_nodes=dp["max_res"])
+            prot = dict(batch=dp["batch"], num_graphs=args.batch, max_nodes=dp["max_res"], protein_embed=embed, dense_index=dense)
             pred, _ = model(prot, molg)
             if count:
                 preds.append(pred)
