@@ -227,7 +227,7 @@ def main():
 
     import torch.distributed as dist
     import caster_dta_b200 as cg
-    from caster_dta_b200 import _lib, parallel
+    from caster_dta_b200 import _lib, ops, parallel
     from caster_dta_b200.configs import caster_dta_2_2
 
     if not torch.cuda.is_available():
@@ -276,6 +276,8 @@ def main():
     torch.manual_seed(9)
     model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"]).to(dev).train()
     model.overlap_encoders = os.environ.get("CGVP_OVERLAP", "1") == "1"
+    if model.overlap_encoders and os.environ.get("CGVP_WGRAD_STREAM", "1") == "1":
+        ops.set_wgrad_stream(torch.cuda.Stream(device=dev))
     parallel.broadcast_parameters(model, 0)
     bucket = parallel.GradSync(model)
     opt = torch.optim.Adam(bucket.params, lr=1e-4, fused=True, capturable=True)
@@ -286,6 +288,7 @@ def main():
         pred, _ = model(prot, molg)
         loss = torch.nn.functional.mse_loss(pred.squeeze(-1), d["y"])
         loss.backward()
+        ops.join_wgrad_stream()
         return loss.detach()
 
     graphs = {}          # id(batch dict) -> GraphedStep replaying zero-grad + forward + backward on that batch's buffers

@@ -14,7 +14,8 @@
 #include "cgvp_common.cuh"
 #include "cgvp_tc.cuh"
 
-#define WG_RB 32                          // rows (reduction steps) per stage = 4 MMA k-blocks; sets the bytes in flight per CTA
+#define WG_RB 16                          // rows (reduction steps) per stage = 2 MMA k-blocks (64 KB of stage buffers at K = 128:
+                                          // small enough to share an SM with other streams' kernels)
 #define WG_NT 512                         // threads per CTA: 16 warps share the split / store work of a stage
 #define WG_NW (WG_NT / 32)
 #define WG_GROUP_BYTES (WG_RB * 128)      // one 32-column group of a stage: [4-step atom][4 steps][128 B]

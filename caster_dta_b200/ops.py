@@ -485,6 +485,21 @@ def _linear_dgrad(dy, w):
     return dx
 
 
+WGRAD_STREAM = None      # optional side stream for the dense-layer weight gradients (set_wgrad_stream / join_wgrad_stream)
+
+
+def set_wgrad_stream(stream):
+    """Run `cgvp_linear_wgrad` on `stream` (None = on the backward's own stream).  The caller must call
+    `join_wgrad_stream()` after `backward()` and before anything reads the parameter gradients."""
+    global WGRAD_STREAM
+    WGRAD_STREAM = stream
+
+
+def join_wgrad_stream():
+    if WGRAD_STREAM is not None:
+        torch.cuda.current_stream().wait_stream(WGRAD_STREAM)
+
+
 class LinearFunction(torch.autograd.Function):
     """y = x w^T + b on the tensor cores with fp32 accuracy (3xTF32, csrc/linear_tc.cu): forward, input gradient and
     weight / bias gradient; shapes outside the kernels' range fall back to the stock GEMMs."""
@@ -499,9 +514,20 @@ class LinearFunction(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = _linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
         dw = db = None
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        side = WGRAD_STREAM
+        if want_w and side is not None:
+            # parameter gradients are leaves of the backward pass: compute them off the critical path (the driver joins
+            # with join_wgrad_stream() after backward, before the optimizer / the end of a graph capture)
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dw, db = linear_wgrad(dy, x, ctx.has_bias)
+            dy.record_stream(side)
+            x.record_stream(side)
+        dx = _linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        if want_w and side is None:
             dw, db = linear_wgrad(dy, x, ctx.has_bias)
         return dx, dw, db
 

@@ -390,6 +390,35 @@ def test_linear_wgrad_tensor_core_vs_fp64(m, n, k):
     assert_close(xg.grad, dy.double() @ w.detach().double(), TIGHT, "dX")
 
 
+def test_linear_wgrad_side_stream_same_bits():
+    """Weight gradients computed on a side stream (ops.set_wgrad_stream) are the same bits as on the main stream."""
+    _mods()
+    from caster_dta_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(5000, 128, generator=g).to(DEV).requires_grad_()
+    w1 = torch.randn(256, 128, generator=g).to(DEV).requires_grad_()
+    b1 = torch.randn(256, generator=g).to(DEV).requires_grad_()
+    w2 = torch.randn(128, 256, generator=g).to(DEV).requires_grad_()
+
+    def run():
+        for t in (x, w1, b1, w2):
+            t.grad = None
+        y = ops.linear(torch.relu(ops.linear(x, w1, b1)), w2)
+        y.square().sum().backward()
+        ops.join_wgrad_stream()
+        torch.cuda.synchronize()
+        return [t.grad.clone() for t in (x, w1, b1, w2)]
+
+    ref = run()
+    ops.set_wgrad_stream(torch.cuda.Stream())
+    try:
+        for _ in range(3):
+            got = run()
+            assert all(torch.equal(a, b) for a, b in zip(ref, got))
+    finally:
+        ops.set_wgrad_stream(None)
+
+
 @pytest.mark.parametrize("rows,d", [(1, 32), (1000, 128), (22806, 128), (4097, 256), (333, 64)])
 def test_row_layernorm_vs_torch(rows, d):
     """csrc/layernorm.cu against nn.LayerNorm in fp64: output, dx, dgamma, dbeta; bit-reproducible."""
