@@ -534,7 +534,7 @@ class LinearFunction(torch.autograd.Function):
 
 def linear(x, w, b=None):
     """`F.linear` for 2-D CUDA activations; large row counts take the tensor-core weight-gradient path."""
-    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and w.dtype == torch.float32:
+    if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and w.dtype == torch.float32 and not torch.is_autocast_enabled():
         m, n, k = x.shape[0], w.shape[0], w.shape[1]
         if torch.is_grad_enabled() and (w.requires_grad or x.requires_grad):
             if linear_wgrad_supported(m, n, k):
