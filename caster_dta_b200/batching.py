@@ -79,13 +79,18 @@ class SizeCappedBatchSampler:
                 yield samples
 
 
-def collate_graphs(graphs):
+def collate_graphs(graphs, emit_plan=None):
     """Batch a list of graphs (dicts of device tensors) into one disconnected graph.
 
     Each dict holds `x` (tensor `[n, F]` or tuple `(s [n,S], V [n,C,3])`), `edge_index [2,e]` int64 and any of
     `edge_attr` (tensor or tuple), `node_type [n]`, `edge_type [e]`.  Returns the same keys concatenated, edge indices
     shifted by the node offsets, plus `batch [N]`, `ptr [B+1]`, `num_graphs`, `max_nodes` (python ints known from the
-    shapes -- no device read)."""
+    shapes -- no device read).
+
+    `emit_plan` (default: when the graphs live on a CUDA device and carry (s, V) features): also build the graph plan
+    of the batched edge list -- the dst-sorted / src-sorted CSR views the fused GVPConv kernels aggregate over
+    (`ops.GraphPlan`, `cgvp_plan_build`) -- and return it under `plan`, so the encoder does not sort the edges again
+    (`JointGNN.forward_with_graphs` / `protein_gnn(..., plan=...)` accept it)."""
     if not graphs:
         raise ValueError("collate_graphs needs at least one graph")
 
@@ -115,4 +120,9 @@ def collate_graphs(graphs):
     out["ptr"] = ptr
     out["num_graphs"] = len(graphs)
     out["max_nodes"] = max(sizes)
+    if emit_plan is None:
+        emit_plan = dev.type == "cuda" and isinstance(graphs[0]["x"], (tuple, list))
+    if emit_plan:
+        from . import ops
+        out["plan"] = ops.GraphPlan(out["edge_index"], ptr_host[-1])
     return out

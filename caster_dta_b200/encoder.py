@@ -62,12 +62,13 @@ class VectorProteinGNN_LBAModel(nn.Module):
                            ln1=(ln.scalar_norm.weight, ln.scalar_norm.bias), weights=g.kernel_weights())
         return out if g.vo else out[0]
 
-    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
+    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None, plan=None):
         x_s, x_v = x[0], x[1]
         if eattr is None:
             raise ValueError("the LBA encoder needs edge attributes (s, V)")
         e_s, e_v = eattr[0], eattr[1]
-        plan = ops.get_plan(edge_index, x_s.shape[0])
+        if plan is None:                     # `plan`: a GraphPlan of this edge_index built earlier (e.g. by the collate)
+            plan = ops.get_plan(edge_index, x_s.shape[0])
         h = self._embed(self.gvp_node, (x_s, x_v), ntypes, self.num_ntypes, getattr(self, "ntype_embedding", None))
         # edge embedding is produced directly in dst-sorted order: both conv layers then stream it contiguously
         e = self._embed(self.gvp_edge, (e_s, e_v), etypes, self.num_etypes, getattr(self, "etype_embedding", None),
@@ -96,8 +97,8 @@ class SelectableProteinModelWrapper(nn.Module):
         self.is_scalar_data = False
         self.gnn_model = VectorProteinGNN_LBAModel(in_channels=in_channels, edge_dim=edge_dim, **kwargs)
 
-    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
-        return self.gnn_model(x, edge_index, ntypes, etypes, eattr=eattr, batch=batch)
+    def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None, plan=None):
+        return self.gnn_model(x, edge_index, ntypes, etypes, eattr=eattr, batch=batch, plan=plan)
 
     def __getattr__(self, name):
         try:

@@ -6,6 +6,7 @@
 and `edge_type [E]` (all zero: the shipped dataset has a single edge type).
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -15,22 +16,43 @@ from .ops import _aligned_ptr, _ptr, _stream, _workspace
 THRESH_TYPES = {"dist": 0, "num": 1, "prop": 2}
 
 
-def residue_graph_batch(res_coords, ptr, edge_thresh=4.0, thresh_type="dist", keep_self_loops=True):
-    """res_coords: [N,4,3] (N, CA, C, O) or [N,3] C-alpha coordinates, fp32, CUDA; ptr: [B+1] int64 boundaries."""
+def knn_edge_count(lengths, edge_thresh, thresh_type="num", keep_self_loops=True):
+    """Edges the 'num' / 'prop' selections produce for proteins of the given lengths (host integers): every residue keeps
+    min(k, candidates) neighbours (`utils/create_protein_features.py:304-327`).  Lets a caller size the outputs without
+    reading the count back from the device (`residue_graph_batch(..., num_edges=...)`)."""
+    if thresh_type not in ("num", "prop"):
+        raise ValueError("the edge count of a radius graph depends on the coordinates")
+    total = 0
+    for n in lengths:
+        n = int(n)
+        k = int(math.ceil(edge_thresh * n)) if thresh_type == "prop" else int(edge_thresh)
+        total += n * max(0, min(k, n - (0 if keep_self_loops else 1)))
+    return total
+
+
+def residue_graph_batch(res_coords, ptr, edge_thresh=4.0, thresh_type="dist", keep_self_loops=True, max_len=None,
+                        num_edges=None):
+    """res_coords: [N,4,3] (N, CA, C, O) or [N,3] C-alpha coordinates, fp32, CUDA; ptr: [B+1] int64 boundaries.
+
+    `max_len` (an upper bound of the longest protein) and `num_edges` (the exact edge count, see `knn_edge_count`) are
+    optional host-side hints: with both given the call makes no device->host read, so it can be captured in a CUDA graph
+    whose `res_coords` / `ptr` buffers are refilled before every replay."""
     if not res_coords.is_cuda:
         raise RuntimeError("the featurizer needs CUDA tensors (there is no CPU fallback)")
     ca = (res_coords[:, 1, :] if res_coords.dim() == 3 else res_coords).contiguous().float()
     ptr = ptr.to(device=ca.device, dtype=torch.int64).contiguous()
     n, b = int(ca.shape[0]), int(ptr.shape[0]) - 1
     code = THRESH_TYPES[thresh_type]
-    max_len = int((ptr[1:] - ptr[:-1]).max()) if b > 0 else 0
+    if max_len is None:
+        max_len = int((ptr[1:] - ptr[:-1]).max()) if b > 0 else 0
+    max_len = int(max_len)
     dev = ca.device
     offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
     ws = _workspace(lib().cgvp_featurize_workspace_bytes(n, max_len), dev)
     wp, wn = _aligned_ptr(ws)
     check(lib().cgvp_featurize_count(_ptr(ca), _ptr(ptr), b, n, max_len, float(edge_thresh), code, int(keep_self_loops),
                                      _ptr(offsets), wp, wn, _stream()), "cgvp_featurize_count")
-    e = int(offsets[-1])                      # the one device->host read of the featurizer
+    e = int(offsets[-1]) if num_edges is None else int(num_edges)      # the one device->host read of the featurizer
     edge_index = torch.empty(2, e, dtype=torch.int64, device=dev)
     edge_s = torch.empty(e, 32, dtype=torch.float32, device=dev)
     edge_v = torch.empty(e, 1, 3, dtype=torch.float32, device=dev)
@@ -84,12 +106,13 @@ def aa_property_table(pd_maps):
 
 
 def protein_graph_batch(res_coords, ptr, res_idents, aa_table=None, edge_thresh=4.0, thresh_type="dist",
-                        keep_self_loops=True, add_residue_posenc=False):
+                        keep_self_loops=True, add_residue_posenc=False, max_len=None, num_edges=None):
     """Backbone coordinates -> the keyword arguments of the protein encoder, all on the device:
     `construct_graph` (`utils/create_graphs.py:6-62`) for every protein + `Batch.from_data_list`
     (`dataset/dual_dataset.py:543`).  `model.protein_gnn(**protein_graph_batch(...))` runs the GVP stack."""
     x = residue_node_features(res_coords, ptr, res_idents, aa_table, add_residue_posenc)
-    edge_index, eattr, etypes = residue_graph_batch(res_coords, ptr, edge_thresh, thresh_type, keep_self_loops)
+    edge_index, eattr, etypes = residue_graph_batch(res_coords, ptr, edge_thresh, thresh_type, keep_self_loops, max_len,
+                                                    num_edges)
     dev = res_coords.device
     ptr = ptr.to(device=dev, dtype=torch.int64)
     n = int(res_coords.shape[0])

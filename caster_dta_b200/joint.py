@@ -78,8 +78,8 @@ class HomoMoleculeGNN_GINE(nn.Module):
     def forward(self, x, edge_index, ntypes, etypes, eattr=None, batch=None):
         x = torch.cat([_one_hot(ntypes, self.num_ntypes, x.dtype), x], -1)
         e = torch.cat([_one_hot(etypes, self.num_etypes, x.dtype), eattr], -1)
-        for conv in self.conv_list[:-1]:
-            x = self.dropout(self.activation(conv(x, edge_index, e)))
+        for k, conv in enumerate(self.conv_list[:-1]):
+            x = ops.dropout(self.dropout, self.activation(conv(x, edge_index, e)), f"gine.{k}")
         return self.activation(self.conv_list[-1](x, edge_index, e))
 
 
@@ -160,9 +160,14 @@ def _lin(mod, x):
     return ops.linear(x, mod.weight, mod.bias) if x.is_cuda and x.dim() == 2 else mod(x)
 
 
-def _seq(mods, x):
+def _seq(mods, x, site=""):
     for m in mods:
-        x = _lin(m, x) if isinstance(m, nn.Linear) else m(x)
+        if isinstance(m, nn.Linear):
+            x = _lin(m, x)
+        elif isinstance(m, nn.Dropout):
+            x = ops.dropout(m, x, site + ".inner")
+        else:
+            x = m(x)
     return x
 
 
@@ -248,7 +253,7 @@ class CrossAttentionModule(nn.Module):
             e1, e2 = a1, a2
         return e1, e2, (w1, w2)
 
-    def forward_packed(self, x1, x2, d1, d2, return_weights=True, first=True):
+    def forward_packed(self, x1, x2, d1, d2, return_weights=True, first=True, site="attn.0"):
         """Same block (`models/joint_gnn.py:321-408`) on packed rows x1 [N1, D1], x2 [N2, D2]; d1 / d2: DenseIndex."""
         n1, n2 = ops.layer_norm(x1, self.preattn_norm1), ops.layer_norm(x2, self.preattn_norm2)
         f1 = self.preattn_norm1.bias if first else None
@@ -258,8 +263,8 @@ class CrossAttentionModule(nn.Module):
             a2, w2 = _mha_packed(self.embed2_to_1, n2, n1, d2, d1, f2, return_weights, self.training)
             if not self.include_residual_stream:
                 return a2, w2
-            y2 = x2 + self.ff_dropout(a2)
-            return y2 + self.ff_dropout(_seq(self.ff2, ops.layer_norm(y2, self.ff_norm2))), w2
+            y2 = x2 + ops.dropout(self.ff_dropout, a2, site + ".a2")
+            return y2 + ops.dropout(self.ff_dropout, _seq(self.ff2, ops.layer_norm(y2, self.ff_norm2), site + ".ff2"), site + ".ff2.outer"), w2
 
         side = self.side_stream if x1.is_cuda else None
         if side is not None:                 # the two directions are independent: run the second on the side stream
@@ -269,8 +274,8 @@ class CrossAttentionModule(nn.Module):
                 y2, w2 = stream2()
         a1, w1 = _mha_packed(self.embed1_to_2, n1, n2, d1, d2, f1, return_weights, self.training)
         if self.include_residual_stream:
-            x1 = x1 + self.ff_dropout(a1)
-            x1 = x1 + self.ff_dropout(_seq(self.ff1, ops.layer_norm(x1, self.ff_norm1)))
+            x1 = x1 + ops.dropout(self.ff_dropout, a1, site + ".a1")
+            x1 = x1 + ops.dropout(self.ff_dropout, _seq(self.ff1, ops.layer_norm(x1, self.ff_norm1), site + ".ff1"), site + ".ff1.outer")
         else:
             x1 = a1
         if side is not None:
@@ -300,7 +305,7 @@ class StackedCrossAttentionModule(nn.Module):
         reference computes from padding and never uses)."""
         weights = []
         for i, layer in enumerate(self.cross_attn_layers):
-            x1, x2, w = layer.forward_packed(x1, x2, d1, d2, return_weights, first=i == 0)
+            x1, x2, w = layer.forward_packed(x1, x2, d1, d2, return_weights, first=i == 0, site=f"attn.{i}")
             weights.append(w)
         return x1, x2, weights
 
@@ -360,6 +365,11 @@ class JointGNN(nn.Module):
     @staticmethod
     def _graphs_to_dicts(protein_graph, molecule_graph):
         def as_dict(g):
+            if isinstance(g, dict):           # the output of `batching.collate_graphs` (PyG `Data` key names + hints + plan)
+                d = {"x": g["x"], "edge_index": g["edge_index"], "ntypes": g["node_type"], "etypes": g["edge_type"],
+                     "eattr": g["edge_attr"], "batch": g["batch"]}
+                d.update({k: g[k] for k in ("num_graphs", "max_nodes", "plan") if k in g})
+                return d
             return {"x": g.x, "edge_index": g.edge_index, "ntypes": g.node_type, "etypes": g.edge_type,
                     "eattr": g.edge_attr, "batch": g.batch}
         return as_dict(protein_graph), as_dict(molecule_graph)
@@ -367,9 +377,9 @@ class JointGNN(nn.Module):
     def forward_with_graphs(self, protein_graph, molecule_graph):
         return self.forward(*self._graphs_to_dicts(protein_graph, molecule_graph))
 
-    def _stack(self, x, lins, norms):
-        for lin, norm in zip(lins, norms):
-            x = self.dropout(self.activation(norm(_lin(lin, x))))
+    def _stack(self, x, lins, norms, site):
+        for k, (lin, norm) in enumerate(zip(lins, norms)):
+            x = ops.dropout(self.dropout, self.activation(norm(_lin(lin, x))), f"{site}.{k}")
         return x
 
     def _pool(self, x, mask):
@@ -385,10 +395,12 @@ class JointGNN(nn.Module):
         pg, mg = dict(protein_graph_data), dict(molecule_graph_data)
         hints_p = {k: pg.pop(k, None) for k in ("num_graphs", "max_nodes")}
         hints_m = {k: mg.pop(k, None) for k in ("num_graphs", "max_nodes")}
+        mg.pop("plan", None)
         # `protein_embed`: residue embeddings computed earlier for the same protein(s) -- the encoder
         # output depends on the protein only, so an inference sweep over many ligands per protein can reuse it
         embed = pg.pop("protein_embed", None)
         dp_cached = pg.pop("dense_index", None)          # optional: the DenseIndex of the same protein batch (see protein_embed)
+        plan = pg.pop("plan", None)                      # optional: the GraphPlan of `edge_index` (batching.collate_graphs emits it)
         # The two encoders are independent (`models/joint_gnn.py:183-190`): the molecule side -- ~60 tiny kernels on ~10^3
         # atoms -- runs on a side stream under the protein encoder's large kernels (fork / join, also inside graph capture;
         # autograd replays each side's backward on the stream of its forward).
@@ -401,14 +413,14 @@ class JointGNN(nn.Module):
             side = self._side_stream
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
+                atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms, "atom_lins")
                 dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
         if embed is None:
-            embed = self.protein_gnn(**pg)
-        res = self._stack(embed, self.residue_lins, self.residue_norms)
+            embed = self.protein_gnn(**pg) if plan is None else self.protein_gnn(plan=plan, **pg)
+        res = self._stack(embed, self.residue_lins, self.residue_norms, "residue_lins")
         dp = dp_cached if dp_cached is not None else DenseIndex(pg.get("batch"), res.shape[0], device=res.device, **hints_p)
         if side is None:
-            atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms)
+            atm = self._stack(self.molecule_gnn(**mg), self.atom_lins, self.atom_norms, "atom_lins")
             dm = DenseIndex(mg.get("batch"), atm.shape[0], device=atm.device, **hints_m)
         else:
             torch.cuda.current_stream().wait_stream(side)
@@ -422,10 +434,12 @@ class JointGNN(nn.Module):
         pe, me = self._pool(dp.pad(res), dp.mask), self._pool(dm.pad(atm), dm.mask)
         if self.include_post_pool_layernorm:
             pe, me = self.protein_post_pool_norm(pe), self.molecule_post_pool_norm(me)
-        pe = self._stack(self.dropout(self.activation(pe)), self.protein_lins, self.protein_norms)
-        me = self._stack(self.dropout(self.activation(me)), self.molecule_lins, self.molecule_norms)
-        x = self.dropout(self.activation(self.pm_embed_lin(torch.cat([pe, me], -1))))
-        x = self._stack(x, self.out_fc_layers, self.out_fc_norms)
+        pe = self._stack(ops.dropout(self.dropout, self.activation(pe), "pool.protein"), self.protein_lins, self.protein_norms,
+                         "protein_lins")
+        me = self._stack(ops.dropout(self.dropout, self.activation(me), "pool.molecule"), self.molecule_lins, self.molecule_norms,
+                         "molecule_lins")
+        x = ops.dropout(self.dropout, self.activation(self.pm_embed_lin(torch.cat([pe, me], -1))), "pm_embed")
+        x = self._stack(x, self.out_fc_layers, self.out_fc_norms, "out_fc")
         return self.output_layer(x), weights
 
 

@@ -162,6 +162,8 @@ class Dropout(nn.Module):
             return None
         ms = self.sdropout(torch.ones(s_shape, device=device))
         mv = self.vdropout.mask(v_shape, device)
+        if ops.MASK_LOG is not None:
+            ops.MASK_LOG.setdefault("gvp", []).append((ms, mv))
         return ms, mv
 
     def forward(self, x):

@@ -38,6 +38,23 @@ def _aligned_ptr(ws, align=256):
     return C.c_void_p((p + align - 1) // align * align), ws.numel() - align
 
 
+# ---- dropout-mask recording (parity tests of train-mode steps) ---------------------------------------------------------
+# None: every dropout site uses its stock path.  A dict: each site draws its keep-mask explicitly (same distribution,
+# `mask / (1 - p)`), applies it by multiplication and leaves the mask under its site name, so that a test can feed the
+# identical masks to the CPU oracle.  Works under CUDA-graph capture (the recorded tensors are the graph's own buffers
+# and hold the masks of the latest replay).
+MASK_LOG = None
+
+
+def dropout(mod, x, site):
+    """`mod(x)` for an `nn.Dropout` module, recording the mask under `site` while MASK_LOG is a dict."""
+    if MASK_LOG is None or not mod.training or mod.p == 0:
+        return mod(x)
+    m = torch.nn.functional.dropout(torch.ones_like(x), mod.p, True)
+    MASK_LOG[site] = m
+    return x * m
+
+
 # ----------------------------------------------------------------------------------------------------------------
 class GvpSpec:
     """Static description of one GVP (`models/gvp_layers.py:123-140`)."""
@@ -149,7 +166,14 @@ _plan_cache = {}
 
 def get_plan(edge_index, num_nodes):
     """Plan cached per edge_index tensor (same storage, shape and version -> same plan), so the two conv layers of
-    a model and repeated steps over the same batch sort the edges once."""
+    a model and repeated eager steps over the same batch sort the edges once.
+
+    While a CUDA graph is being captured the cache is bypassed in both directions: the graph will be replayed after
+    the caller has refilled `edge_index` with another batch, so `cgvp_plan_build` has to be part of the captured work
+    (a cached plan would silently keep the old perm / rowptr), and a plan built on graph-private memory must not be
+    handed to later eager calls."""
+    if edge_index.is_cuda and torch.cuda.is_current_stream_capturing():
+        return GraphPlan(edge_index, num_nodes)
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), edge_index.device.index)
     hit = _plan_cache.get(key)
     if hit is not None and hit[0]() is not None:

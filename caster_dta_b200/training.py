@@ -1,0 +1,134 @@
+"""The training step of CASTER-DTA (`train_model.py:555-575`: forward, MSE loss, backward, optimizer step) on fixed-shape
+("bucketed") batches, replayed as ONE CUDA graph per bucket.
+
+Everything between the arrival of a padded batch in device memory and the updated weights is inside the captured
+work -- nothing is cached across batches:
+
+    coordinates -> node features + kNN residue graph + edge features   (featurizer.protein_graph_batch)
+                -> dst-sorted / src-sorted CSR plan                      (cgvp_plan_build)
+                -> JointGNN forward -> weighted MSE over the real pairs -> backward
+                -> gradient pack + ONE all-reduce (NCCL) + fused Adam     (parallel.FlatAdam)
+
+A replay after copying another batch of the same bucket into the static input buffers therefore computes that batch's
+step (`tests/test_gpu_parity.py::test_bucketed_graph_step_matches_oracle_on_two_batches`).
+"""
+import types
+
+import torch
+
+from . import ops
+from .featurizer import knn_edge_count, protein_graph_batch
+
+INPUT_KEYS = ("coords", "idents", "ptr", "m_x", "m_ei", "m_ea", "m_nt", "m_et", "m_batch", "y", "w")
+
+
+def bucket_key(meta, edge_thresh, thresh_type, keep_self_loops=True):
+    """Everything that fixes the shapes (and launch geometry) of a step: padded sizes, edge count, length bounds."""
+    e = knn_edge_count(meta["lengths"], edge_thresh, thresh_type, keep_self_loops)
+    return (meta["slots"], meta["n_pad"], e, meta["a_pad"], meta["me_pad"])
+
+
+class BucketedTrainStep:
+    """`step(batch)` runs one optimizer step on a padded device batch (dict of tensors with `INPUT_KEYS`, see
+    `loader.pad_pairs`) and returns the loss tensor (device, not synchronised).
+
+    launch_mode "graph": one captured CUDA graph per bucket key (captured on first use, all graphs share one memory
+    pool); "eager": the same work launched kernel by kernel."""
+
+    def __init__(self, model, flat_adam, aa_table, edge_thresh=30, thresh_type="num", keep_self_loops=True,
+                 max_len=1056, max_atoms=128, launch_mode="graph", update=True, capture_warmup=2, record_masks=False):
+        if thresh_type not in ("num", "prop"):
+            raise ValueError("fixed-shape steps need an edge count known on the host: 'num' or 'prop' graphs")
+        self.model, self.opt = model, flat_adam
+        self.dev = next(model.parameters()).device
+        self.aa_table = aa_table.to(self.dev)
+        self.edge_thresh, self.thresh_type, self.keep_self_loops = edge_thresh, thresh_type, keep_self_loops
+        self.max_len, self.max_atoms = int(max_len), int(max_atoms)
+        self.launch_mode, self.update = launch_mode, update      # update=False: gradients only, no optimizer step (tests)
+        self.capture_warmup = capture_warmup
+        self.graphs = {}            # bucket key -> namespace(graph, static, loss, pred, masks)
+        self.pool = None
+        self.record_masks = record_masks      # parity tests: every dropout site leaves its mask (ops.MASK_LOG)
+        self.last_masks = None
+
+    # ---- the work of one step on the tensors of `b` -------------------------------------------------------------------
+    def body(self, b, num_edges, slots, warm=False):
+        """`warm`: capture warm-up -- everything except the collective and the weight update, so that ranks which capture
+        different buckets at different times neither wait for each other nor let their replicas drift apart."""
+        prot = protein_graph_batch(b["coords"], b["ptr"], b["idents"], self.aa_table, self.edge_thresh, self.thresh_type,
+                                   self.keep_self_loops, max_len=self.max_len, num_edges=num_edges)
+        prot.update(num_graphs=slots, max_nodes=self.max_len)
+        mol = dict(x=b["m_x"], edge_index=b["m_ei"], ntypes=b["m_nt"], etypes=b["m_et"], eattr=b["m_ea"], batch=b["m_batch"],
+                   num_graphs=slots, max_nodes=self.max_atoms)
+        pred, _ = self.model(prot, mol)
+        err = pred.squeeze(-1) - b["y"]
+        loss = (b["w"] * err * err).sum()          # mean-squared error over the real pairs (dummy pairs weigh 0)
+        self.opt.reset()
+        loss.backward()
+        ops.join_wgrad_stream()
+        self.opt.sync(collective=not warm)
+        if self.update and not warm:
+            self.opt.step()
+        return loss.detach(), pred.detach()
+
+    def _check(self, meta):
+        if meta["max_len"] > self.max_len or meta["max_atoms"] > self.max_atoms:
+            raise ValueError(f"batch exceeds the step's bounds: longest protein {meta['max_len']} > {self.max_len} or "
+                             f"largest ligand {meta['max_atoms']} > {self.max_atoms}")
+
+    def key_of(self, meta):
+        return bucket_key(meta, self.edge_thresh, self.thresh_type, self.keep_self_loops)
+
+    def prepare(self, batch, meta):
+        """Capture the graph of this batch's bucket if it does not exist yet (its warm-up runs forward + backward only: no
+        collective, no weight update)."""
+        self._check(meta)
+        key = self.key_of(meta)
+        if self.launch_mode == "graph" and key not in self.graphs:
+            self._capture(key, batch)
+        return key
+
+    def step(self, batch, meta):
+        key = self.prepare(batch, meta)
+        if self.launch_mode != "graph":
+            if self.record_masks:
+                ops.MASK_LOG = {}
+            try:
+                loss, self.last_pred = self.body(batch, key[2], key[0])
+                self.last_masks = ops.MASK_LOG
+            finally:
+                ops.MASK_LOG = None
+            return loss
+        entry = self.graphs[key]
+        for k in INPUT_KEYS:
+            entry.static[k].copy_(batch[k], non_blocking=True)
+        entry.graph.replay()
+        self.last_pred, self.last_masks = entry.pred, entry.masks
+        return entry.loss
+
+    def _capture(self, key, batch):
+        static = {k: batch[k].clone() for k in INPUT_KEYS}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        masks = None
+        try:
+            if self.record_masks:
+                ops.MASK_LOG = {}
+            with torch.cuda.stream(side):             # warm-up on a side stream (allocator, cuBLAS handles, lazy inits)
+                for _ in range(self.capture_warmup):
+                    self.body(static, key[2], key[0], warm=True)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            if self.record_masks:
+                ops.MASK_LOG = masks = {}
+            graph = torch.cuda.CUDAGraph()
+            kw = {} if self.pool is None else {"pool": self.pool}
+            with torch.cuda.graph(graph, **kw):
+                loss, pred = self.body(static, key[2], key[0])
+        finally:
+            ops.MASK_LOG = None
+        if self.pool is None:
+            self.pool = graph.pool()
+        self.graphs[key] = types.SimpleNamespace(graph=graph, static=static, loss=loss, pred=pred, masks=masks)
+        return self.graphs[key]

@@ -17,6 +17,8 @@ Fixtures:
   lba_checkpoint.npz protein-GNN slice of the shipped checkpoint (15 117 parameters) + a small synthetic batch
                      (radius 4 A and kNN-10 graphs) + the reference embeddings [N,64].
   joint_small.npz    a reduced-width JointGNN (random init, seed 9): state_dict, batch, predicted affinity.
+  joint_checkpoint.npz  the WHOLE shipped checkpoint (764 396 parameters) + two small batches (radius 4 A, kNN-30) + the
+                     reference's predicted affinities, residue embeddings and attention maps (fp64, and fp32 predictions).
   sampler.json       mini-batches produced by the reference PMD_BatchSampler (dataset/dual_dataset.py:424-522) on a
                      seeded list of pair sizes, several settings, shuffle off.
 """
@@ -343,6 +345,65 @@ def make_joint_small():
     print("joint_small.npz", len(store), "arrays")
 
 
+def make_joint_checkpoint():
+    """The WHOLE shipped checkpoint (764 396 parameters, `pretrained_model_downstream/bestvalmodel_*.pt`) loaded the way
+    `inference/inference_utils.py:40-68` does, evaluated the way `inference/evaluation.py:43-46` does (eval mode,
+    `forward_with_graphs`-equivalent call, predictions un-standardised with `dataset_rescale_params.json`) on two small
+    synthetic batches: radius 4 A + self loops (the checkpoint's own graph type, `dataset_kwargs.json`) and kNN-30
+    (BASELINE config 1).  The weights travel inside the fixture (fp32), so the GPU box needs no reference checkout."""
+    root = os.path.join(ref_shim.REFERENCE_ROOT, "pretrained_model_downstream")
+    kw = json.load(open(os.path.join(root, "model_kwargs.json")))
+    rescale = json.load(open(os.path.join(root, "dataset_rescale_params.json")))["standardize"]
+    ck = [f for f in sorted(os.listdir(root)) if f.startswith("bestvalmodel")][0]
+    sd = torch.load(os.path.join(root, ck), weights_only=True, map_location="cpu")
+    sd = {k.replace("_orig_mod.", ""): v for k, v in sd.items()}
+    model = JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"])
+    model.load_state_dict(sd)
+    model.eval()
+    store = {"kwargs_json": np.frombuffer(json.dumps(kw).encode(), dtype=np.uint8)}
+    for k, v in sd.items():
+        store["model/param/" + k] = v.numpy()
+    put(store, "rescale", mean=rescale["scale_mean_factor"], std=rescale["scale_std_factor"])
+    for case, (thr, tt, pairs, lo, hi, seed) in {"radius4": (4.0, "dist", 4, 90, 260, 41), "knn30": (30, "num", 3, 60, 110, 43)}.items():
+        rng = np.random.default_rng(seed)
+        xs, xv, nts, eis, ess, evs, batch = [], [], [], [], [], [], []
+        off = 0
+        for k in range(pairs):
+            n = int(rng.integers(lo, hi))
+            coords = synth.random_backbone(n, rng, self_avoiding=(tt == "dist"))
+            idents = rng.integers(0, 20, size=n)
+            d = reference_graph(coords, idents, thr, tt, True)
+            xs.append(d.x[0]); xv.append(d.x[1]); nts.append(d.node_type)
+            eis.append(d.edge_index + off); ess.append(d.edge_attr[0]); evs.append(d.edge_attr[1])
+            batch.append(torch.full((n,), k, dtype=torch.long))
+            off += n
+        ei = torch.cat(eis, 1)
+        prot = dict(x=(torch.cat(xs), torch.cat(xv)), edge_index=ei, ntypes=torch.cat(nts),
+                    etypes=torch.zeros(ei.shape[1], dtype=torch.long), eattr=(torch.cat(ess), torch.cat(evs)), batch=torch.cat(batch))
+        mol = {k: torch.from_numpy(v) for k, v in synth.molecule_batch(pairs, seed=seed).items()}
+        outs = {}
+        for name, dt in (("fp64", torch.float64), ("fp32", torch.float32)):
+            model.to(dt)
+            pd = dict(x=(prot["x"][0].to(dt), prot["x"][1].to(dt)), edge_index=prot["edge_index"], ntypes=prot["ntypes"],
+                      etypes=prot["etypes"], eattr=(prot["eattr"][0].to(dt), prot["eattr"][1].to(dt)), batch=prot["batch"])
+            md = dict(x=mol["x"].to(dt), edge_index=mol["edge_index"], ntypes=mol["ntypes"], etypes=mol["etypes"],
+                      eattr=mol["eattr"].to(dt), batch=mol["batch"])
+            with torch.no_grad():
+                pred, attn = model(pd, md)
+                emb = model.protein_gnn(**pd)
+            outs[name] = (pred, attn, emb)
+        model.float()
+        pred, attn, emb = outs["fp64"]
+        put(store, case + "/prot", x_s=prot["x"][0], x_v=prot["x"][1], edge_index=prot["edge_index"], ntypes=prot["ntypes"],
+            etypes=prot["etypes"], e_s=prot["eattr"][0], e_v=prot["eattr"][1], batch=prot["batch"])
+        put(store, case + "/mol", **mol)
+        put(store, case + "/out", pred=pred, affinity=pred * rescale["scale_std_factor"] + rescale["scale_mean_factor"],
+            residue_embed=emb, attn_p2m=attn[0][0], attn_m2p=attn[0][1], pred_fp32=outs["fp32"][0])
+        print(case, "pred", pred.flatten().tolist(), "fp32-fp64", float((outs["fp32"][0].double() - pred).abs().max()))
+    np.savez_compressed(os.path.join(HERE, "joint_checkpoint.npz"), **store)
+    print("joint_checkpoint.npz", len(store), "arrays")
+
+
 def make_sampler():
     """`dataset/dual_dataset.py` imports mdtraj / rdkit at module level, so the sampler class alone is compiled from
     its own source text (located with `ast`, executed unchanged) and driven with a stand-in dataset."""
@@ -388,8 +449,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sampler":
         make_sampler()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "joint_checkpoint":
+        make_joint_checkpoint()
+        sys.exit(0)
     make_gvp_units()
     make_featurizer()
     make_lba_checkpoint()
     make_joint_small()
+    make_joint_checkpoint()
     make_sampler()

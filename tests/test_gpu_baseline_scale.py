@@ -1,0 +1,280 @@
+"""GPU parity at BASELINE scale: the compositions and shapes `bench.py` actually runs, against the CPU oracle and the
+reference-generated fixtures.
+
+* the WHOLE shipped checkpoint's affinities (config 1; `inference/inference_utils.py:40-68`, `evaluation.py:43-46`);
+* the featurizer on 300-2 000-residue proteins, kNN-30 and radius 4 A (`utils/create_protein_features.py:290-327`);
+* the backward pass THROUGH dropout of a GVPConvLayer (`models/gvp_layers.py:177-219,407-410`);
+* bench's exact step -- CUDA-graph replay of featurizer + plan build + forward + backward + all-reduce + Adam on a
+  bucket-padded Davis-shape batch of 32 pairs (N ~ 2 x 10^4, E ~ 6 x 10^5), dropout on, molecule encoder and dense-layer
+  weight gradients on side streams, conv stash -- against the oracle fed the same dropout masks, on TWO different
+  batches replayed through the SAME captured graph (a stale plan / cached graph state would fail the second one).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, case, golden, json_blob
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _fp32_matmul():
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _dev_dicts(pr, mo):
+    prot = dict(x=(pr["x_s"].float().to(DEV), pr["x_v"].float().to(DEV)), edge_index=pr["edge_index"].to(DEV),
+                ntypes=pr["ntypes"].to(DEV), etypes=pr["etypes"].to(DEV),
+                eattr=(pr["e_s"].float().to(DEV), pr["e_v"].float().to(DEV)), batch=pr["batch"].to(DEV))
+    mol = dict(x=mo["x"].float().to(DEV), edge_index=mo["edge_index"].to(DEV), ntypes=mo["ntypes"].to(DEV),
+               etypes=mo["etypes"].to(DEV), eattr=mo["eattr"].float().to(DEV), batch=mo["batch"].to(DEV))
+    return prot, mol
+
+
+@pytest.mark.parametrize("name", ["radius4", "knn30"])
+def test_full_checkpoint_affinities_golden(name):
+    """JointGNN(model_kwargs.json) + the shipped 764 396-parameter checkpoint (keys with the `_orig_mod.` prefix handled by
+    `load_state_dict_from_checkpoint`, strict) -> predicted affinities within 1e-4 of the reference's."""
+    import caster_dta_b200 as cg
+    g = golden("joint_checkpoint")
+    kw = json_blob(g)
+    model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"])
+    sd = {"_orig_mod." + k: v for k, v in case(g, "model")["param"].items()}          # as the file on disk has them
+    cg.load_state_dict_from_checkpoint(model, sd, strict=True)
+    assert sum(p.numel() for p in model.parameters()) == 764396
+    model.to(DEV).eval()
+    prot, mol = _dev_dicts(case(g, name + "/prot"), case(g, name + "/mol"))
+    out = case(g, name + "/out")
+    with torch.no_grad():
+        pred, weights = model(prot, mol)
+        emb = model.protein_gnn(**prot)
+    assert_close(emb, out["residue_embed"], 2e-5, "residue embedding")
+    assert_close(pred, out["pred"], TOL, "standardised affinity")
+    rs = case(g, "rescale")
+    aff = pred.double().cpu() * float(rs["std"]) + float(rs["mean"])                  # dataset.unscale_target
+    assert_close(aff, out["affinity"], TOL, "affinity (pKd)")
+    assert_close(weights[0][0], out["attn_p2m"], TOL, "attention residues->atoms")
+    # real (unpadded) part of the atoms->residues map, as evaluation.py:56-58 slices it
+    ref = out["attn_m2p"]
+    got = weights[0][1].cpu()
+    nb = int(prot["batch"].max()) + 1
+    plen = torch.bincount(prot["batch"].cpu(), minlength=nb)
+    mlen = torch.bincount(mol["batch"].cpu(), minlength=nb)
+    for b in range(nb):
+        assert_close(got[b, :mlen[b], :plen[b]], ref[b, :mlen[b], :plen[b]], TOL, f"attention atoms->residues, pair {b}")
+
+
+@pytest.mark.parametrize("thresh,ttype", [(30, "num"), (4.0, "dist")])
+def test_featurizer_baseline_shapes_vs_oracle(thresh, ttype):
+    """8 proteins of 300-2 000 residues featurized as ONE batch: edge_index / directions bit-exact, RBF / pos-enc <= 1 ulp.
+    kNN-30 at these lengths takes the multi-digit radix-select path of `csrc/featurize.cu`."""
+    import caster_dta_b200 as cg
+    from caster_dta_b200 import synth
+    from caster_dta_b200.featurizer import knn_edge_count
+    from oracle import featurizer_oracle
+    rng = np.random.default_rng(2024)
+    lens = [300, 2000, 1999, 517] + [int(x) for x in rng.integers(300, 2001, size=4)]
+    cs = [synth.random_backbone(n, rng, self_avoiding=False) for n in lens]
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum(lens)]))
+    coords = torch.from_numpy(np.concatenate(cs)).to(DEV)
+    ei, (es, ev), et = cg.residue_graph_batch(coords, ptr, thresh, ttype, True)
+    refs = [featurizer_oracle.residue_graph(c, thresh, ttype, True) for c in cs]
+    off = np.cumsum([0] + lens[:-1])
+    ref_ei = np.concatenate([r[0] + o for r, o in zip(refs, off)], 1)
+    assert np.array_equal(ei.cpu().numpy(), ref_ei), "edge_index must be bit-exact"
+    ref_v = np.concatenate([r[2] for r in refs])
+    assert np.array_equal(ev.cpu().numpy(), ref_v), "direction vectors must be bit-exact"
+    ref_s = torch.from_numpy(np.concatenate([r[1] for r in refs]))
+    got = es.cpu()
+    ulp = (got.view(torch.int32) - ref_s.view(torch.int32)).abs()
+    close = (got - ref_s).abs() <= 1e-7
+    assert bool(((ulp <= 1) | close).all()), f"scalar features differ by more than 1 ulp (max {int(ulp.max())})"
+    if ttype == "num":
+        # the capture-safe call (host-side hints instead of device->host reads) gives the same graph
+        e = knn_edge_count(lens, thresh, ttype, True)
+        assert e == ref_ei.shape[1]
+        ei2, (es2, ev2), _ = cg.residue_graph_batch(coords, ptr, thresh, ttype, True, max_len=2048, num_edges=e)
+        assert torch.equal(ei, ei2) and torch.equal(es, es2) and torch.equal(ev, ev2)
+
+
+@pytest.mark.parametrize("n,e,aggr", [(1500, 40000, "sum"), (400, 9000, "mean")])
+def test_conv_layer_dropout_backward_vs_oracle(n, e, aggr):
+    """Train mode, drop_rate 0.2: outputs AND every gradient (inputs, edge attributes, 38 parameter tensors) of a
+    GVPConvLayer against the oracle fed with the masks the CUDA path drew (recorded through ops.MASK_LOG)."""
+    import caster_dta_b200 as cg
+    from caster_dta_b200 import ops
+    from oracle import gvp_oracle
+    import torch.nn.functional as F
+    from test_gpu_parity import _random_layer_case, _leaf
+    nd, ed = (16, 4), (32, 1)
+    p, ei, x, ea = _random_layer_case(n, e, nd, ed, seed=n + e, hub=True, aggr=aggr)
+    m = cg.GVPConvLayer(nd, ed, drop_rate=0.2, activations=(F.relu, None), vector_gate=True, aggr=aggr)
+    m.load_state_dict(p, strict=True)
+    m.to(DEV).train()
+    xs, xv, es, ev = _leaf(x[0]), _leaf(x[1]), _leaf(ea[0]), _leaf(ea[1])
+    torch.manual_seed(123)
+    ops.MASK_LOG = {}
+    try:
+        out = m((xs, xv), ei.to(DEV), (es, ev))
+        masks = ops.MASK_LOG["gvp"]
+    finally:
+        ops.MASK_LOG = None
+    assert len(masks) == 2 and float((masks[0][0] == 0).float().mean()) > 0.1, "dropout must be active"
+    g = torch.Generator().manual_seed(7)
+    cs, cv = torch.randn(out[0].shape, generator=g), torch.randn(out[1].shape, generator=g)
+    ((out[0] * cs.to(DEV)).sum() + (out[1] * cv.to(DEV)).sum()).backward()
+    p64 = {k: v.double().requires_grad_(v.numel() > 0) for k, v in p.items()}
+    l64 = [t.double().requires_grad_() for t in (x[0], x[1], ea[0], ea[1])]
+    dm = tuple((a.cpu().double(), b.cpu().double()) for a, b in masks)
+    ref = gvp_oracle.gvp_conv_layer(p64, "", (l64[0], l64[1]), ei, (l64[2], l64[3]), aggr=aggr, scalar_act="relu",
+                                    vector_act=None, vector_gate=True, drop_masks=dm)
+    ((ref[0] * cs.double()).sum() + (ref[1] * cv.double()).sum()).backward()
+    assert_close(out[0], ref[0], TOL, "s")
+    assert_close(out[1], ref[1], TOL, "V")
+    for t, r, k in zip((xs, xv, es, ev), l64, ("grad_s", "grad_v", "grad_es", "grad_ev")):
+        assert_close(t.grad, r.grad, TOL, k, atol=1e-6)
+    for name, prm in m.named_parameters():
+        if prm.numel():
+            assert_close(prm.grad, p64[name].grad, TOL, "grad " + name, atol=1e-5)
+
+
+def _train_setup(launch_mode, seed=9):
+    import caster_dta_b200 as cg
+    from caster_dta_b200 import loader, ops, parallel, training
+    from caster_dta_b200.configs import caster_dta_2_2
+    kw = caster_dta_2_2()
+    torch.manual_seed(seed)
+    model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"]).to(DEV).train()
+    model.overlap_encoders = True                                   # bench.py's settings
+    ops.set_wgrad_stream(torch.cuda.Stream())
+    opt = parallel.FlatAdam(model, lr=1e-4)
+    return kw, model, opt, loader, training
+
+
+def _oracle_step(kw, names, snapshot, t, aa_table, masks, thresh=30, ttype="num"):
+    """Loss and parameter gradients of the same step on the CPU oracle in fp64, fed with the recorded masks."""
+    from oracle import pipeline
+    p64 = {k: (v.double().requires_grad_(v.numel() > 0) if v.dtype.is_floating_point else v) for k, v in snapshot.items()}
+    prot = pipeline.featurize_batch(t["coords"].numpy(), t["ptr"].numpy(), t["idents"].numpy(), aa_table, thresh, ttype, True,
+                                    torch.float64)
+    mol = pipeline.molecule_dict(t, torch.float64)
+    gm = masks["gvp"]
+    gvp_masks = [((gm[2 * k][0].cpu().double(), gm[2 * k][1].cpu().double()),
+                  (gm[2 * k + 1][0].cpu().double(), gm[2 * k + 1][1].cpu().double())) for k in range(len(gm) // 2)] or None
+    dm = {k: v.cpu().double() for k, v in masks.items() if k != "gvp"}
+    loss, pred = pipeline.train_loss(p64, kw, prot, mol, t["y"].double(), t["w"].double(), gvp_masks, dm, training=True)
+    loss.backward()
+    return float(loss), pred.detach(), {n: p64[n].grad for n in names}, prot
+
+
+def _compare_step(tag, kw, model, opt, snapshot, t, aa_table, masks, loss, pred, pairs):
+    names = [n for n, p in model.named_parameters() if p.requires_grad and p.numel() > 0]
+    assert len(names) == 158 and len(opt.params) == 158
+    ref_loss, ref_pred, ref_grads, prot = _oracle_step(kw, names, snapshot, t, aa_table, masks)
+    assert abs(float(loss) - ref_loss) <= TOL * abs(ref_loss), f"{tag}: loss {float(loss)} vs oracle {ref_loss}"
+    assert_close(pred[:pairs], ref_pred[:pairs], TOL, tag + " predictions")
+    gscale = max(float(g.abs().max()) for g in ref_grads.values())
+    for n, g in zip(names, opt.grads()):
+        assert_close(g, ref_grads[n], TOL, f"{tag}: grad {n}", atol=1e-6 * gscale)
+    return prot
+
+
+def test_bucketed_graph_step_matches_oracle_on_two_batches():
+    kw, model, opt, loader, training = _train_setup("graph")
+    from caster_dta_b200 import ops
+    try:
+        ds = loader.SyntheticPairDataset("davis", 32 * 5, seed=9)
+        batches = list(loader.PairBatchLoader(ds, max_num=16_000_000, max_bsize=32, shuffle=False))
+        (ta, ma), (tb, mb) = batches[2], batches[4]
+        key = training.bucket_key(ma, 30, "num")
+        assert key == training.bucket_key(mb, 30, "num") and ma["nodes"] != mb["nodes"], "the two batches must share a bucket"
+        assert ma["nodes"] > 19000 and key[2] > 600000, "Davis-shape scale"
+        step = training.BucketedTrainStep(model, opt, torch.from_numpy(ds.aa_table), 30, "num", True, max_len=1056,
+                                          max_atoms=128, launch_mode="graph", record_masks=True)
+        names = list(model.state_dict().keys())
+        for tag, t, meta in (("batch A", ta, ma), ("batch B", tb, mb)):
+            dev = {k: v.to(DEV) for k, v in t.items()}
+            step.prepare(dev, meta)                                  # capture on first use (its warm-up steps move the weights)
+            torch.cuda.synchronize()
+            snapshot = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            loss = step.step(dev, meta)
+            torch.cuda.synchronize()
+            assert len(step.graphs) == 1, "both batches must replay the same captured graph"
+            masks = step.last_masks
+            _compare_step(tag, kw, model, opt, snapshot, t, ds.aa_table, masks, loss.cpu(), step.last_pred.cpu(), meta["pairs"])
+            after = model.state_dict()
+            moved = max(float((after[k].cpu() - snapshot[k]).abs().max()) for k in names if snapshot[k].numel())
+            assert moved > 0, "the captured step must include the optimizer update"
+    finally:
+        ops.set_wgrad_stream(None)
+
+
+def test_eager_and_graph_steps_agree_and_dummy_pairs_are_inert():
+    """Small shapes: (1) the eager step equals the oracle; (2) padding a batch into a LARGER bucket (more filler residues /
+    atoms in the dummy pair) leaves the real pairs' predictions and the gradients unchanged up to fp32 summation order."""
+    kw, model, opt, loader, training = _train_setup("eager", seed=3)
+    from caster_dta_b200 import ops
+    try:
+        ds = loader.SyntheticPairDataset("tiny", 12, seed=4, edge_thresh=10)
+        res = {}
+        for gran in (256, 1024):
+            spec = loader.BucketSpec(7, node_gran=gran, atom_gran=gran // 4, mol_edge_gran=512)
+            t, meta = next(iter(loader.PairBatchLoader(ds, max_num=10_000_000, max_bsize=6, spec=spec, shuffle=False)))
+            step = training.BucketedTrainStep(model, opt, torch.from_numpy(ds.aa_table), 10, "num", True, max_len=1200,
+                                              max_atoms=300, launch_mode="eager", update=False)
+            model.eval()                                             # no dropout: the two paddings must then agree
+            snapshot = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+            dev = {k: v.to(DEV) for k, v in t.items()}
+            loss = step.step(dev, meta)
+            torch.cuda.synchronize()
+            res[gran] = (float(loss), step.last_pred.cpu()[:meta["pairs"]].clone(), [g.cpu().clone() for g in opt.grads()])
+            if gran == 256:
+                _compare_step("eager", kw, model, opt, snapshot, t, ds.aa_table, {"gvp": []}, loss.cpu(), step.last_pred.cpu(),
+                              meta["pairs"])
+        a, b = res[256], res[1024]
+        assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0])
+        assert_close(b[1], a[1], 1e-5, "predictions with a larger dummy pair")
+        for x, y in zip(a[2], b[2]):
+            assert_close(y, x, 1e-4, "gradient with a larger dummy pair", atol=1e-7)
+    finally:
+        ops.set_wgrad_stream(None)
+
+
+def test_collate_emits_the_plan_and_feeds_forward_with_graphs():
+    """N4: `collate_graphs` on device tensors returns the dst-sorted plan of the batched edge list; `forward_with_graphs`
+    consumes the collated dicts (plan included) and matches a forward pass that builds its own plan."""
+    import caster_dta_b200 as cg
+    from caster_dta_b200 import batching, ops, synth
+    from caster_dta_b200.configs import caster_dta_2_2
+    kw = caster_dta_2_2()
+    torch.manual_seed(5)
+    model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"]).to(DEV).eval()
+    rng = np.random.default_rng(8)
+    pg, mg = [], []
+    for n in (57, 130, 91):
+        c = torch.from_numpy(synth.random_backbone(n, rng)).to(DEV)
+        ptr = torch.tensor([0, n])
+        d = cg.protein_graph_batch(c, ptr, torch.from_numpy(rng.integers(0, 20, size=n)),
+                                   torch.from_numpy(rng.random((20, 11)).astype(np.float32)), 10, "num", True)
+        pg.append(dict(x=d["x"], edge_index=d["edge_index"], edge_attr=d["eattr"], node_type=d["ntypes"], edge_type=d["etypes"]))
+        x, ei, ea, nt, et = synth.random_molecule(rng)
+        mg.append(dict(x=torch.from_numpy(x).to(DEV), edge_index=torch.from_numpy(ei).to(DEV), edge_attr=torch.from_numpy(ea).to(DEV),
+                       node_type=torch.from_numpy(nt).to(DEV), edge_type=torch.from_numpy(et).to(DEV)))
+    pb, mb = batching.collate_graphs(pg), batching.collate_graphs(mg)
+    assert "plan" in pb and "plan" not in mb
+    fresh = ops.GraphPlan(pb["edge_index"], 57 + 130 + 91)
+    for name in ("perm", "src", "dst", "rowptr", "sperm", "srowptr"):
+        assert torch.equal(getattr(pb["plan"], name), getattr(fresh, name)), name
+    order = torch.argsort(pb["edge_index"][1], stable=True)
+    assert torch.equal(pb["plan"].perm.long(), order)
+    with torch.no_grad():
+        a, _ = model.forward_with_graphs(pb, mb)
+        pb2 = {k: v for k, v in pb.items() if k != "plan"}
+        b, _ = model.forward_with_graphs(pb2, mb)
+    assert torch.equal(a, b)

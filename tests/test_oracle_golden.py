@@ -135,6 +135,26 @@ def test_joint_small():
     assert_close(weights[0][1], out["attn_m2p"], 1e-11)
 
 
+@pytest.mark.parametrize("name", ["radius4", "knn30"])
+def test_joint_full_checkpoint(name):
+    """Oracle fed with the WHOLE shipped checkpoint reproduces the reference's affinities (config 1)."""
+    g = golden("joint_checkpoint")
+    kw = json_blob(g)
+    p = {k: v.double() if v.dtype.is_floating_point else v for k, v in case(g, "model")["param"].items()}
+    assert sum(v.numel() for v in p.values()) == 764396
+    pr, mo, out = case(g, name + "/prot"), case(g, name + "/mol"), case(g, name + "/out")
+    prot = dict(x=(pr["x_s"].double(), pr["x_v"].double()), edge_index=pr["edge_index"], ntypes=pr["ntypes"],
+                etypes=pr["etypes"], eattr=(pr["e_s"].double(), pr["e_v"].double()), batch=pr["batch"])
+    mol = dict(x=mo["x"].double(), edge_index=mo["edge_index"], ntypes=mo["ntypes"], etypes=mo["etypes"],
+               eattr=mo["eattr"].double(), batch=mo["batch"])
+    pred, weights = joint_oracle.joint_forward(p, kw, prot, mol)
+    assert_close(pred, out["pred"], 1e-11)
+    assert_close(weights[0][0], out["attn_p2m"], 1e-10)
+    rs = case(g, "rescale")
+    assert_close(pred * float(rs["std"]) + float(rs["mean"]), out["affinity"], 1e-11)
+    assert_close(out["pred_fp32"], out["pred"], 1e-4)           # the reference's own fp32 run sits inside the tolerance
+
+
 FEAT_SETTINGS = ["dist4_self", "dist8_noself", "num10_self", "num8_noself", "prop_self", "num_gt_n"]
 
 

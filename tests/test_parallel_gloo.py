@@ -87,3 +87,41 @@ def test_shard_by_cost_balances():
     loads = [sum(costs[i] for i in p) for p in parts]
     assert sorted(i for p in parts for i in p) == list(range(8))
     assert abs(loads[0] - loads[1]) <= 15
+
+
+def _worker_flat_adam(rank, world, port, ret):
+    """parallel.FlatAdam over gloo: globally-normalised shard losses, SUM all-reduce on the flat buffer, one fused update;
+    the replicas end bit-identical and equal to a single process that trains on the whole batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(321 + rank)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    parallel.broadcast_parameters(model, 0)
+    start = {k: v.clone() for k, v in model.state_dict().items()}
+    opt = parallel.FlatAdam(model, lr=1e-2, capturable=False)
+    data = torch.randn(8, 6, generator=torch.Generator().manual_seed(7))
+    mine = parallel.shard_pairs(8, rank, world)
+    for _ in range(3):
+        opt.reset()
+        (model(data[mine]).square().sum() / 8).backward()           # weights 1 / GLOBAL batch
+        opt.sync()
+        opt.step()
+    ref_model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 1))
+    ref_model.load_state_dict(start)
+    ref_opt = torch.optim.Adam(ref_model.parameters(), lr=1e-2)
+    for _ in range(3):
+        ref_opt.zero_grad(set_to_none=True)
+        ref_model(data).square().mean().backward()
+        ref_opt.step()
+    ref = torch.cat([p.detach().flatten() for p in ref_model.parameters()])
+    ret[rank] = (float((opt.flat_param.detach() - ref).abs().max()), opt.flat_param.detach().tolist())
+    dist.destroy_process_group()
+
+
+def test_flat_adam_world2_matches_single_process():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_flat_adam, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] < 1e-6 and ret[1][0] < 1e-6
+    assert ret[0][1] == ret[1][1], "replicas must hold bit-identical weights"
