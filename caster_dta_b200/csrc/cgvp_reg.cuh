@@ -141,7 +141,9 @@ struct Save {
     float sg[1][G::VO1];    // the factor they were multiplied with                            :163 / :166
 };
 
-template <class G>
+// GIVEN_SP: sv.sp already holds s' (e.g. read back from a training stash): the W_s projection -- most of a GVP's scalar
+// arithmetic -- is skipped and `s` is not read; everything else (Vh, norms, Vo, gate) is recomputed from v and s'.
+template <class G, bool GIVEN_SP = false>
 CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::SI], const float (&v)[3][G::VI1],
                             float (&so)[1][G::SO], float (&vout)[3][G::VO1], Save<G>& sv) {
     if constexpr (G::VI > 0) {
@@ -153,10 +155,12 @@ CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::
             sv.vn[0][o] = sqrtf(fmaxf(q, CGVP_EPS));
         }
     }
+    if constexpr (!GIVEN_SP) {
 #pragma unroll
-    for (int o = 0; o < G::SO; ++o) sv.sp[0][o] = W[G::O_WS_T + G::KSD * G::SOP + o];      // bias row
-    mv<G::SI, G::SO, G::SOP, 0, 0>(W + G::O_WS_T, s, sv.sp);
-    if constexpr (G::VI > 0) mv<G::H, G::SO, G::SOP, 0, 0>(W + G::O_WS_T + G::SI * G::SOP, sv.vn, sv.sp);
+        for (int o = 0; o < G::SO; ++o) sv.sp[0][o] = W[G::O_WS_T + G::KSD * G::SOP + o];      // bias row
+        mv<G::SI, G::SO, G::SOP, 0, 0>(W + G::O_WS_T, s, sv.sp);
+        if constexpr (G::VI > 0) mv<G::H, G::SO, G::SOP, 0, 0>(W + G::O_WS_T + G::SI * G::SOP, sv.vn, sv.sp);
+    }
 #pragma unroll
     for (int o = 0; o < G::SO; ++o) so[0][o] = actf<G::SACT>(sv.sp[0][o]);                  // :172-173
     if constexpr (G::VO > 0) {

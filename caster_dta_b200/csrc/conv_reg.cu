@@ -25,7 +25,7 @@ struct ConvRegArgs {
     const float *d_out_s, *d_out_v;
     float *d_e_s, *d_e_v, *dj;
     float* partial;                       // [gridDim.x][PF] weight-gradient partials
-    float* stash;                         // [E][STASH] outputs of message GVPs 0 and 1 per sorted edge (forward writes, backward reads) or NULL
+    float* stash;                         // [E][STASH] training stash per sorted edge (forward writes, backward reads) or NULL
 };
 
 template <int NS_, int NV_, int ES_, int EV_, class G0_, class G1_, class G2_>
@@ -38,7 +38,9 @@ struct ConvSpec {
     static constexpr int SO = G2::SO, VO = G2::VO;
     static constexpr int CH = SO + 3 * VO;        // message channels = output node row
     static constexpr int CHX = NS + 3 * NV;       // node row (gradient slices)
-    static constexpr int ST1 = G0::SO + 3 * G0::VO, ST2 = G1::SO + 3 * G1::VO, STASH = ST1 + ST2;   // stage-input stash row
+    // training stash row per sorted edge: [s'_0 ; V_1 ; s'_1 ; V_2 ; s'_2] -- the PRE-activation scalars of the three message
+    // GVPs (the stage inputs follow by the activation) and the vector stage inputs: the backward skips every W_s projection
+    static constexpr int ST1 = G0::SO + 3 * G0::VO, ST2 = G1::SO + 3 * G1::VO, STASH = ST1 + ST2 + G2::SO;
     // shared-memory weight offsets (floats)
     static constexpr int WF0 = 0, WF1 = G0::FWD_FLOATS, WF2 = WF1 + G1::FWD_FLOATS, WF = WF2 + G2::FWD_FLOATS;
     static constexpr int WT0 = 0, WT1 = G0::TOTAL_FLOATS, WT2 = WT1 + G1::TOTAL_FLOATS, WT = WT2 + G2::TOTAL_FLOATS;
@@ -91,24 +93,34 @@ __global__ void __launch_bounds__(CR_THREADS, 2) conv_fwd_reg_kernel(const __gri
         const long long p = lane < rv ? p0 + lane : p0;          // idle lanes replay the first row (never stored)
         const int src = __ldg(a.src + p), dst = __ldg(a.dst + p);
         const long long eid = a.edge_sorted ? p : (long long)__ldg(a.perm + p);
+        const bool stash = a.stash && lane < rv;                // training: the backward reads these instead of recomputing them
+        float* srow = a.stash + p * S::STASH;
         float s1[1][G0::SO], v1[3][G0::VO1];
         {
             float s0[1][G0::SI], v0[3][G0::VI1];
             load_message_input<S>(a, src, dst, eid, s0, v0);
             Save<G0> sv;
             gvp_fwd<G0>(wsm + S::WF0, s0, v0, s1, v1, sv);
+            if (stash) {
+                store_s<G0::SO, 0>(srow, 0, sv.sp, false);
+                store_v<G0::VO, 0>(srow + G0::SO, 0, v1, false);
+            }
         }
         float s2[1][G1::SO], v2[3][G1::VO1];
-        { Save<G1> sv; gvp_fwd<G1>(wsm + S::WF1, s1, v1, s2, v2, sv); }
-        if (a.stash && lane < rv) {                             // training: the backward reads these instead of recomputing them
-            float* row = a.stash + p * S::STASH;
-            store_s<G0::SO, 0>(row, 0, s1, false);
-            store_v<G0::VO, 0>(row + G0::SO, 0, v1, false);
-            store_s<G1::SO, 0>(row + S::ST1, 0, s2, false);
-            store_v<G1::VO, 0>(row + S::ST1 + G1::SO, 0, v2, false);
+        {
+            Save<G1> sv;
+            gvp_fwd<G1>(wsm + S::WF1, s1, v1, s2, v2, sv);
+            if (stash) {
+                store_s<G1::SO, 0>(srow + S::ST1, 0, sv.sp, false);
+                store_v<G1::VO, 0>(srow + S::ST1 + G1::SO, 0, v2, false);
+            }
         }
         float s3[1][G2::SO], v3[3][G2::VO1];
-        { Save<G2> sv; gvp_fwd<G2>(wsm + S::WF2, s2, v2, s3, v3, sv); }
+        {
+            Save<G2> sv;
+            gvp_fwd<G2>(wsm + S::WF2, s2, v2, s3, v3, sv);
+            if (stash) store_s<G2::SO, 0>(srow + S::ST1 + S::ST2, 0, sv.sp, false);
+        }
 #pragma unroll
         for (int c = 0; c < S::SO; ++c) M[c * CGVP_WPITCH + lane] = s3[0][c];
 #pragma unroll
@@ -170,22 +182,40 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __gri
         const int src = __ldg(a.src + p), dst = __ldg(a.dst + p);
         const long long eid = a.edge_sorted ? p : (long long)__ldg(a.perm + p);
         WarpSink sink{reinterpret_cast<float4*>(stgf), arena, lane, valid};
-        // forward chain, keeping only the stage inputs (each GVP is recomputed right before its backward)
-        float s1[1][G0::SO], v1[3][G0::VO1], s2[1][G1::SO], v2[3][G1::VO1];
+        // pre-activation scalars s'_k of the three message GVPs and the vector stage inputs: from the forward's training
+        // stash, or from a forward chain.  Each GVP's remaining internals (Vh, norms, Vo, gate) are recomputed right before
+        // its backward; its W_s projection is not (gvp_fwd<G, true>).
+        float sp0[1][G0::SO], v1[3][G0::VO1], sp1[1][G1::SO], v2[3][G1::VO1], sp2[1][G2::SO];
         if (a.stash) {                                            // written by the forward pass of the same call pair
             const float* row = a.stash + p * S::STASH;
-            load_s<G0::SO, 0>(row, 0, s1);
+            load_s<G0::SO, 0>(row, 0, sp0);
             load_v<G0::VO, 0>(row + G0::SO, 0, v1);
-            load_s<G1::SO, 0>(row + S::ST1, 0, s2);
+            load_s<G1::SO, 0>(row + S::ST1, 0, sp1);
             load_v<G1::VO, 0>(row + S::ST1 + G1::SO, 0, v2);
+            load_s<G2::SO, 0>(row + S::ST1 + S::ST2, 0, sp2);
         } else {
+            float s1[1][G0::SO], s2[1][G1::SO];
             {
                 float s0[1][G0::SI], v0[3][G0::VI1];
                 load_message_input<S>(a, src, dst, eid, s0, v0);
                 Save<G0> sv;
                 gvp_fwd<G0>(wsm + S::WT0, s0, v0, s1, v1, sv);
+#pragma unroll
+                for (int c = 0; c < G0::SO; ++c) sp0[0][c] = sv.sp[0][c];
             }
-            { Save<G1> sv; gvp_fwd<G1>(wsm + S::WT1, s1, v1, s2, v2, sv); }
+            {
+                Save<G1> sv;
+                gvp_fwd<G1>(wsm + S::WT1, s1, v1, s2, v2, sv);
+#pragma unroll
+                for (int c = 0; c < G1::SO; ++c) sp1[0][c] = sv.sp[0][c];
+            }
+            {
+                Save<G2> sv;
+                float so[1][G2::SO], vo[3][G2::VO1];
+                gvp_fwd<G2>(wsm + S::WT2, s2, v2, so, vo, sv);
+#pragma unroll
+                for (int c = 0; c < G2::SO; ++c) sp2[0][c] = sv.sp[0][c];
+            }
         }
         // d(message_e) = d_out[dst_e] (/ deg for mean)
         float gs3[1][S::SO], gv3[3][G2::VO1];
@@ -203,8 +233,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __gri
         float gs2[1][G1::SO], gv2[3][G1::VO1];
         {
             Save<G2> sv;
-            float so[1][G2::SO], vo[3][G2::VO1], dsin[1][G2::KSD], dvin[3][G2::VI1];
-            gvp_fwd<G2>(wsm + S::WT2, s2, v2, so, vo, sv);
+            float s2[1][G1::SO], so[1][G2::SO], vo[3][G2::VO1], dsin[1][G2::KSD], dvin[3][G2::VI1];
+#pragma unroll
+            for (int c = 0; c < G1::SO; ++c) s2[0][c] = actf<G1::SACT>(sp1[0][c]);
+#pragma unroll
+            for (int c = 0; c < G2::SO; ++c) sv.sp[0][c] = sp2[0][c];
+            gvp_fwd<G2, true>(wsm + S::WT2, s2, v2, so, vo, sv);
             gvp_bwd<G2>(wsm + S::WT2, sv, s2, v2, gs3, gv3, sink, S::GO2, dsin, dvin);
 #pragma unroll
             for (int c = 0; c < G2::SI; ++c) gs2[0][c] = dsin[0][c];
@@ -216,8 +250,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __gri
         float gs1[1][G0::SO], gv1[3][G0::VO1];
         {
             Save<G1> sv;
-            float so[1][G1::SO], vo[3][G1::VO1], dsin[1][G1::KSD], dvin[3][G1::VI1];
-            gvp_fwd<G1>(wsm + S::WT1, s1, v1, so, vo, sv);
+            float s1[1][G0::SO], so[1][G1::SO], vo[3][G1::VO1], dsin[1][G1::KSD], dvin[3][G1::VI1];
+#pragma unroll
+            for (int c = 0; c < G0::SO; ++c) s1[0][c] = actf<G0::SACT>(sp0[0][c]);
+#pragma unroll
+            for (int c = 0; c < G1::SO; ++c) sv.sp[0][c] = sp1[0][c];
+            gvp_fwd<G1, true>(wsm + S::WT1, s1, v1, so, vo, sv);
             gvp_bwd<G1>(wsm + S::WT1, sv, s1, v1, gs2, gv2, sink, S::GO1, dsin, dvin);
 #pragma unroll
             for (int c = 0; c < G1::SI; ++c) gs1[0][c] = dsin[0][c];
@@ -232,7 +270,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_bwd_reg_kernel(const __gri
             load_message_input<S>(a, src, dst, eid, s0, v0);
             Save<G0> sv;
             float so[1][G0::SO], vo[3][G0::VO1];
-            gvp_fwd<G0>(wsm + S::WT0, s0, v0, so, vo, sv);
+#pragma unroll
+            for (int c = 0; c < G0::SO; ++c) sv.sp[0][c] = sp0[0][c];
+            gvp_fwd<G0, true>(wsm + S::WT0, s0, v0, so, vo, sv);
             gvp_bwd<G0>(wsm + S::WT0, sv, s0, v0, gs1, gv1, sink, S::GO0, dsin, dvin);
         }
         if (valid) {

@@ -532,6 +532,9 @@ class LinearFunction(torch.autograd.Function):
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
+        # the side stream is only safe when autograd merely STORES the returned gradients (leaf parameters): a sliced weight
+        # (e.g. a third of nn.MultiheadAttention.in_proj_weight) sends them through more backward kernels on the main stream
+        ctx.side_ok = w.is_leaf and (b is None or b.is_leaf)
         return _linear_fwd(x, w, b)
 
     @staticmethod
@@ -540,7 +543,7 @@ class LinearFunction(torch.autograd.Function):
         dy = dy.contiguous()
         dw = db = None
         want_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
-        side = WGRAD_STREAM
+        side = WGRAD_STREAM if ctx.side_ok else None
         if want_w and side is not None:
             # parameter gradients are leaves of the backward pass: compute them off the critical path (the driver joins
             # with join_wgrad_stream() after backward, before the optimizer / the end of a graph capture)

@@ -109,21 +109,27 @@ class FlatAdam:
     The loss is expected to be normalised by the GLOBAL number of pairs (each rank's weights are 1 / global pairs), so
     the all-reduce is a plain sum and the result equals the single-process gradient of the global batch."""
 
+    ALIGN = 128          # floats
+
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, capturable=True):
         self.params = [p for p in module.parameters() if p.requires_grad and p.numel() > 0]
         self.group = process_group
         self.numel = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat_param = torch.empty(self.numel, dtype=ref.dtype, device=ref.device)
-        self.flat_grad = torch.zeros_like(self.flat_param)
-        off = 0
-        self.grad_views = []
+        # every parameter starts on a 512-byte boundary of the flat buffers (what the caching allocator would give it): the
+        # kernels' 16-byte vector loads of weights / LayerNorm vectors keep working; the padding stays zero
+        offs, total = [], 0
         for p in self.params:
+            offs.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat_param = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.grad_views = []
+        for p, off in zip(self.params, offs):
             n = p.numel()
             self.flat_param[off: off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off: off + n].view_as(p)
             self.grad_views.append(self.flat_grad[off: off + n].view_as(p))
-            off += n
         self.master = torch.nn.Parameter(self.flat_param)
         self.master.grad = self.flat_grad
         fused = ref.is_cuda

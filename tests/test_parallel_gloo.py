@@ -114,7 +114,8 @@ def _worker_flat_adam(rank, world, port, ret):
         ref_model(data).square().mean().backward()
         ref_opt.step()
     ref = torch.cat([p.detach().flatten() for p in ref_model.parameters()])
-    ret[rank] = (float((opt.flat_param.detach() - ref).abs().max()), opt.flat_param.detach().tolist())
+    mine_flat = torch.cat([p.detach().flatten() for p in opt.params])
+    ret[rank] = (float((mine_flat - ref).abs().max()), opt.flat_param.detach().tolist())
     dist.destroy_process_group()
 
 
