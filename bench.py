@@ -451,9 +451,18 @@ def main():
         dist.all_gather_object(gathered, shapes)
     else:
         gathered = [shapes]
-    if rank != 0:
+    def finish():
+        """Leave without hanging: drop the graphs that captured the all-reduce, then tear the process group down."""
+        for st in (stepper, eager):
+            st.close()
         if world > 1:
-            dist.destroy_process_group()
+            clean = parallel.shutdown()
+            sys.stdout.flush(); sys.stderr.flush()
+            if not clean:
+                os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------------------
@@ -523,8 +532,7 @@ def main():
         "reference_gpu": ref_gpu,
     }
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

@@ -169,6 +169,19 @@ class FlatAdam:
         return self.grad_views
 
 
+def shutdown(timeout=20.0):
+    """Destroy the default process group without risking a hang at exit: the caller first drops every CUDA graph that
+    captured a collective (`BucketedTrainStep.close()`); the destruction itself runs in a helper thread and is abandoned
+    after `timeout` seconds."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    import threading
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout)
+    return not t.is_alive()
+
+
 def broadcast_parameters(module, src=0, process_group=None):
     """Replicas start from rank `src`'s weights."""
     if not (dist.is_available() and dist.is_initialized()):

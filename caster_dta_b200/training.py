@@ -106,6 +106,14 @@ class BucketedTrainStep:
         self.last_pred, self.last_masks = entry.pred, entry.masks
         return entry.loss
 
+    def close(self):
+        """Drop the captured graphs.  Call before `torch.distributed.destroy_process_group()`: a live CUDA graph that captured
+        NCCL collectives keeps the communicator in use and its destruction blocks."""
+        self.graphs.clear()
+        self.pool = None
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+
     def _capture(self, key, batch):
         static = {k: batch[k].clone() for k in INPUT_KEYS}
         cur = torch.cuda.current_stream()
