@@ -141,9 +141,14 @@ struct Save {
     float sg[1][G::VO1];    // the factor they were multiplied with                            :163 / :166
 };
 
-// GIVEN_SP: sv.sp already holds s' (e.g. read back from a training stash): the W_s projection -- most of a GVP's scalar
-// arithmetic -- is skipped and `s` is not read; everything else (Vh, norms, Vo, gate) is recomputed from v and s'.
-template <class G, bool GIVEN_SP = false>
+// SPM (how s' = W_s [s ; vn] + b is formed):
+//   0  computed here from all of `s`;
+//   1  sv.sp already holds s' (e.g. read back from a training stash): the W_s projection -- most of a GVP's scalar
+//      arithmetic -- is skipped and `s` is not read; everything else (Vh, norms, Vo, gate) is recomputed from v and s';
+//   2  sv.sp already holds the bias and the contribution of the scalar inputs OUTSIDE [S0, S0 + SN) (e.g. the per-node
+//      projections of the source / target scalars of a message, computed once per node instead of once per edge): only
+//      rows [S0, S0 + SN) of `s` and the norm rows are added here.
+template <class G, int SPM = 0, int S0 = 0, int SN = G::SI>
 CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::SI], const float (&v)[3][G::VI1],
                             float (&so)[1][G::SO], float (&vout)[3][G::VO1], Save<G>& sv) {
     if constexpr (G::VI > 0) {
@@ -155,10 +160,14 @@ CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::
             sv.vn[0][o] = sqrtf(fmaxf(q, CGVP_EPS));
         }
     }
-    if constexpr (!GIVEN_SP) {
+    if constexpr (SPM == 0) {
 #pragma unroll
         for (int o = 0; o < G::SO; ++o) sv.sp[0][o] = W[G::O_WS_T + G::KSD * G::SOP + o];      // bias row
         mv<G::SI, G::SO, G::SOP, 0, 0>(W + G::O_WS_T, s, sv.sp);
+        if constexpr (G::VI > 0) mv<G::H, G::SO, G::SOP, 0, 0>(W + G::O_WS_T + G::SI * G::SOP, sv.vn, sv.sp);
+    } else if constexpr (SPM == 2) {
+        static_assert(S0 >= 0 && S0 + SN <= G::SI, "gvp_fwd: scalar slice out of range");
+        mv<SN, G::SO, G::SOP, S0, 0>(W + G::O_WS_T + S0 * G::SOP, s, sv.sp);
         if constexpr (G::VI > 0) mv<G::H, G::SO, G::SOP, 0, 0>(W + G::O_WS_T + G::SI * G::SOP, sv.vn, sv.sp);
     }
 #pragma unroll
@@ -204,11 +213,17 @@ CGVP_HD inline void gvp_fwd(const float* __restrict__ W, const float (&s)[1][G::
 // On entry gs / gv hold the gradient of the GVP outputs; on exit dsin = [dS_in ; dvn] and dvin = dV_in.
 // NEED_DX = false (the GVP reads leaf data, e.g. the raw edge / node features): only the weight gradients are wanted,
 // so dS_in and dV_in are not formed (dvn still is: it feeds dW_h).
-template <class G, class Sink, bool NEED_DX = true>
-CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, const float (&s)[1][G::SI],
-                            const float (&v)[3][G::VI1], const float (&gs)[1][G::SO], const float (&gv)[3][G::VO1],
-                            Sink& sink, int goff, float (&dsin)[1][G::KSD], float (&dvin)[3][G::VI1]) {
+// Slice mode (S0, SN with SN < SI; the partner of gvp_fwd<G, 2, S0, SN>): only rows [S0, S0 + SN) of the scalar input are
+// handled per row -- their weight-gradient rows, their dS_in columns -- plus the norm rows; the remaining scalar inputs and
+// the bias are handled by the caller from `ds_out` = dL/ds' (e.g. reduced per node first: W^T (sum_e ds'_e), (sum_e ds'_e) x s_n).
+template <class G, class Sink, bool NEED_DX = true, int S0 = 0, int SN = G::SI>
+CGVP_HD inline void gvp_bwd_ds(const float* __restrict__ W, const Save<G>& sv, const float (&s)[1][G::SI],
+                               const float (&v)[3][G::VI1], const float (&gs)[1][G::SO], const float (&gv)[3][G::VO1],
+                               Sink& sink, int goff, float (&dsin)[1][G::KSD], float (&dvin)[3][G::VI1],
+                               float (&ds)[1][G::SO]) {
     constexpr bool HASV = G::VI > 0 && G::VO > 0;
+    constexpr bool SLICE = SN < G::SI;
+    static_assert(S0 >= 0 && S0 + SN <= G::SI && (!SLICE || S0 % 4 == 0), "gvp_bwd: scalar slice");
     float dvo[3][G::VO1], dg[1][G::VO1];
     if constexpr (HASV) {
 #pragma unroll
@@ -231,7 +246,6 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         }
     }
     // ds' = dS_out * sact'(s_out) + (dg . wsv) * vact'(gate input)
-    float ds[1][G::SO];
 #pragma unroll
     for (int o = 0; o < G::SO; ++o) ds[0][o] = gs[0][o] * actb<G::SACT>(actf<G::SACT>(sv.sp[0][o]));
     if constexpr (G::GATE) {
@@ -247,7 +261,7 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         gi1[0][G::SO] = 1.f;
         sink.template add<G::KSV, G::VO, 1>(goff + G::O_WSV_T, gi1, dg);
     }
-    {
+    if constexpr (!SLICE) {
         float a[1][G::KS];
 #pragma unroll
         for (int k = 0; k < G::SI; ++k) a[0][k] = s[0][k];
@@ -257,9 +271,20 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         }
         a[0][G::KSD] = 1.f;
         sink.template add<G::KS, G::SO, 1>(goff + G::O_WS_T, a, ds);
+    } else {
+        float a[1][SN];
+#pragma unroll
+        for (int k = 0; k < SN; ++k) a[0][k] = s[0][S0 + k];
+        sink.template add<SN, G::SO, 1>(goff + G::O_WS_T + S0 * G::SOP, a, ds);
+        if constexpr (G::VI > 0) sink.template add<G::H, G::SO, 1>(goff + G::O_WS_T + G::SI * G::SOP, sv.vn, ds);
     }
     zero2(dsin);
-    if constexpr (NEED_DX || G::VI == 0) {
+    if constexpr (SLICE) {
+        constexpr int C0 = G::SI / 4 * 4;                                   // dvn columns (from a 16-byte boundary)
+        static_assert(S0 + SN <= C0, "gvp_bwd: scalar slice overlaps the norm columns' block");
+        if constexpr (NEED_DX) mv<G::SO, SN, G::KSDP, 0, S0>(W + G::O_WS_B + S0, ds, dsin);
+        if constexpr (G::VI > 0) mv<G::SO, G::KSD - C0, G::KSDP, 0, C0>(W + G::O_WS_B + C0, ds, dsin);
+    } else if constexpr (NEED_DX || G::VI == 0) {
         if constexpr (NEED_DX) mv<G::SO, G::KSD, G::KSDP, 0, 0>(W + G::O_WS_B, ds, dsin);   // [dS_in ; dvn] = ds' . ws
     } else {
         constexpr int C0 = G::SI / 4 * 4;                                   // dvn columns only (from a 16-byte boundary)
@@ -283,6 +308,14 @@ CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, cons
         zero2(dvin);
         if constexpr (NEED_DX) mv<G::H, G::VI, G::VIP, 0, 0>(W + G::O_WH_B, dvh, dvin);     // dV_in = wh^T dVh
     }
+}
+
+template <class G, class Sink, bool NEED_DX = true>
+CGVP_HD inline void gvp_bwd(const float* __restrict__ W, const Save<G>& sv, const float (&s)[1][G::SI],
+                            const float (&v)[3][G::VI1], const float (&gs)[1][G::SO], const float (&gv)[3][G::VO1],
+                            Sink& sink, int goff, float (&dsin)[1][G::KSD], float (&dvin)[3][G::VI1]) {
+    float ds[1][G::SO];
+    gvp_bwd_ds<G, Sink, NEED_DX>(W, sv, s, v, gs, gv, sink, goff, dsin, dvin, ds);
 }
 
 // ---- LayerNorm (gvp_layers.py:231-242) --------------------------------------------------------------------------

@@ -7,13 +7,14 @@ using namespace cgvp;
 
 int conv_fwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, float* out_s, float* out_v, float* part_head,
-                     float* part_tail, float* stash, cudaStream_t st, int* rc_out);
+                     float* part_tail, float* node_ws, float* stash, cudaStream_t st, int* rc_out);
+int64_t conv_special_node_floats(const CgvpConvDesc* desc);
 int64_t conv_special_stash_floats(const CgvpConvDesc* desc);
 int conv_bwd_special(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
                      const float* e_v, const float* const* h_packed, const float* d_out_s, const float* d_out_v,
                      float* d_x_s, float* d_x_v, float* d_e_s, float* d_e_v, int accumulate_edge, float* part_head,
-                     float* part_tail, float* dj, float* partial, int max_grid, const float* stash, cudaStream_t st, int* grid_out,
-                     int* rc_out);
+                     float* part_tail, float* dj, float* partial, int max_grid, float* node_ws, const float* stash, cudaStream_t st,
+                     int* grid_out, int* rc_out);
 
 int64_t conv_tc_workspace_bytes(const CgvpConvDesc* desc, int64_t E, int64_t N);
 int conv_fwd_tc(const CgvpConvDesc* desc, const CgvpPlan* plan, const float* x_s, const float* x_v, const float* e_s,
@@ -417,8 +418,11 @@ static int conv_geometry(ConvK& K, int smem_max, bool backward, size_t* smem_byt
     return -1;
 }
 
+// `node_floats`: per-node scratch of the specialised kernels (per-node projections / reductions of message GVP 0), in floats
+// per node; it sits at the end so that the other offsets do not depend on it.
 static int64_t conv_ws_layout(const ConvK& K, int64_t E, int64_t N, bool backward, int grid, int64_t* o_head,
-                              int64_t* o_tail, int64_t* o_cnt, int64_t* o_dj, int64_t* o_partial, int64_t* o_reduced) {
+                              int64_t* o_tail, int64_t* o_cnt, int64_t* o_dj, int64_t* o_partial, int64_t* o_reduced,
+                              int64_t node_floats = 0, int64_t* o_node = nullptr) {
     const int64_t ntiles_max = cdiv64(E > 0 ? E : 1, 8);
     const int CH = (K.so + 3 * K.vo) > (K.ns + 3 * K.nv) ? (K.so + 3 * K.vo) : (K.ns + 3 * K.nv);
     int64_t off = 0;
@@ -431,6 +435,8 @@ static int64_t conv_ws_layout(const ConvK& K, int64_t E, int64_t N, bool backwar
     if (backward) off += align_up((int64_t)grid * K.partial_floats * 4, 256);
     *o_reduced = off;
     if (backward) off += align_up((int64_t)K.partial_floats * 4, 256);
+    if (o_node) *o_node = off;
+    off += align_up((N > 0 ? N : 1) * node_floats * 4, 256);
     return off + 256;
 }
 
@@ -441,7 +447,7 @@ extern "C" int64_t cgvp_conv_workspace_bytes(const CgvpConvDesc* desc, int64_t n
     const int sms = cgvp_num_sms() > 0 ? cgvp_num_sms() : 148;
     int64_t a, b, c, d, e, f;
     // the tensor-core forward (conv_tc.cu) keeps its own region after the common layout
-    return conv_ws_layout(K, num_edges, num_nodes, backward != 0, 4 * sms, &a, &b, &c, &d, &e, &f) +
+    return conv_ws_layout(K, num_edges, num_nodes, backward != 0, 4 * sms, &a, &b, &c, &d, &e, &f, conv_special_node_floats(desc)) +
            (backward ? 0 : conv_tc_workspace_bytes(desc, num_edges, num_nodes));
 }
 
@@ -479,14 +485,16 @@ extern "C" int32_t cgvp_conv_fwd_stash(const CgvpConvDesc* desc, const CgvpPlan*
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t E = plan->num_edges, N = plan->num_nodes;
     if (E > 0 && N > 0) {   // specialised kernels for the dims they were compiled for (conv_tc.cu, conv_reg.cu)
-        int64_t oh, ot, oc, od, op, orr;
-        const int64_t need = conv_ws_layout(K, E, N, false, 4 * (cgvp_num_sms() > 0 ? cgvp_num_sms() : 148), &oh, &ot, &oc, &od, &op, &orr);
+        int64_t oh, ot, oc, od, op, orr, on;
+        const int64_t need = conv_ws_layout(K, E, N, false, 4 * (cgvp_num_sms() > 0 ? cgvp_num_sms() : 148), &oh, &ot, &oc, &od, &op, &orr,
+                                            conv_special_node_floats(desc), &on);
         if (ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0) {
             char* base = reinterpret_cast<char*>(ws);
             int rc = 0;
             if (conv_fwd_tc(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, base + need, ws_bytes - need, st, &rc)) return rc;
             if (conv_fwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, out_s, out_v, reinterpret_cast<float*>(base + oh),
-                                 reinterpret_cast<float*>(base + ot), reinterpret_cast<float*>(stash), st, &rc))
+                                 reinterpret_cast<float*>(base + ot), reinterpret_cast<float*>(base + on),
+                                 reinterpret_cast<float*>(stash), st, &rc))
                 return rc;
         }
     }
@@ -553,19 +561,20 @@ extern "C" int32_t cgvp_conv_bwd_stash(const CgvpConvDesc* desc, const CgvpPlan*
     const int64_t E = plan->num_edges, N = plan->num_nodes;
     if (E > 0 && N > 0 && plan->sperm && plan->srowptr) {   // specialised register-resident kernel (conv_reg.cu)
         const int sms_ = cgvp_num_sms();
-        int64_t oh, ot, oc, od, op, orr;
-        const int64_t need = conv_ws_layout(K, E, N, true, sms_, &oh, &ot, &oc, &od, &op, &orr);
+        int64_t oh, ot, oc, od, op, orr, on;
+        // partial rows: one per CTA of the edge kernel (<= SMs) + one per CTA of the node-level kernel (<= 2 SMs)
+        const int64_t need = conv_ws_layout(K, E, N, true, 3 * sms_, &oh, &ot, &oc, &od, &op, &orr, conv_special_node_floats(desc), &on);
         if (ws && ws_bytes >= need && ((uintptr_t)ws & 255) == 0) {
             char* base = reinterpret_cast<char*>(ws);
             float* dj = reinterpret_cast<float*>(base + od);
             float* partial = reinterpret_cast<float*>(base + op);
             int rc = 0, grid = 0;
+            // the specialised path does everything up to the per-CTA partials: edge kernel, target / source side reductions,
+            // node-level finish
             if (conv_bwd_special(desc, plan, x_s, x_v, e_s, e_v, h_packed, d_out_s, d_out_v, d_x_s, d_x_v, d_e_s, d_e_v,
                                  accumulate_edge, reinterpret_cast<float*>(base + oh), reinterpret_cast<float*>(base + ot), dj,
-                                 partial, sms_, reinterpret_cast<const float*>(stash), st, &grid, &rc)) {
-                if (rc) return rc;
-                rc = cgvp_segment_reduce_split(dj, K.ns + 3 * K.nv, plan->srowptr, plan->sperm, N, CGVP_AGGR_SUM, 1, d_x_s,
-                                               K.ns, d_x_v, 3 * K.nv, st);
+                                 partial, 3 * sms_, reinterpret_cast<float*>(base + on), reinterpret_cast<const float*>(stash), st,
+                                 &grid, &rc)) {
                 if (rc) return rc;
                 CgvpSeg seg[CGVP_MAX_SEGS];
                 memset(seg, 0, sizeof(seg));

@@ -115,7 +115,7 @@ class BucketedTrainStep:
             torch.cuda.synchronize(self.dev)
 
     def _capture(self, key, batch):
-        static = {k: batch[k].clone() for k in INPUT_KEYS}
+        static = {k: batch[k].to(self.dev, copy=True) for k in INPUT_KEYS}
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(cur)
@@ -140,3 +140,121 @@ class BucketedTrainStep:
             self.pool = graph.pool()
         self.graphs[key] = types.SimpleNamespace(graph=graph, static=static, loss=loss, pred=pred, masks=masks)
         return self.graphs[key]
+
+
+class BucketedInferenceStep:
+    """Affinity prediction (`inference/evaluation.py:43-46`: eval mode, no gradients) on padded batches, one CUDA graph per
+    bucket: featurizer + plan build + protein encoder + ligand encoder + cross attention + head.
+
+    Unique-protein cache: the protein encoder's output depends on the protein only, so a sweep that pairs
+    each protein batch with several ligand batches calls `embed_proteins` once (graph A: coordinates -> residue embeddings +
+    the packed <-> padded row map) and `predict_cached` per ligand batch (graph B: ligand encoder + cross attention + head on
+    the cached embeddings)."""
+
+    def __init__(self, model, aa_table, edge_thresh=30, thresh_type="num", keep_self_loops=True, max_len=2080, max_atoms=130,
+                 launch_mode="graph", capture_warmup=1):
+        if thresh_type not in ("num", "prop") and launch_mode == "graph":
+            raise ValueError("fixed-shape graphs need an edge count known on the host ('num' / 'prop'); use launch_mode='eager'")
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.aa_table = aa_table.to(self.dev)
+        self.edge_thresh, self.thresh_type, self.keep_self_loops = edge_thresh, thresh_type, keep_self_loops
+        self.max_len, self.max_atoms = int(max_len), int(max_atoms)
+        self.launch_mode, self.capture_warmup = launch_mode, capture_warmup
+        self.graphs, self.pool = {}, None
+
+    PROT_KEYS = ("coords", "idents", "ptr")
+    MOL_KEYS = ("m_x", "m_ei", "m_ea", "m_nt", "m_et", "m_batch")
+
+    def _edges(self, meta):
+        if self.thresh_type == "dist":
+            return None
+        return knn_edge_count(meta["lengths"], self.edge_thresh, self.thresh_type, self.keep_self_loops)
+
+    def _protein_dict(self, b, num_edges, slots):
+        prot = protein_graph_batch(b["coords"], b["ptr"], b["idents"], self.aa_table, self.edge_thresh, self.thresh_type,
+                                   self.keep_self_loops, max_len=self.max_len if num_edges is not None else None,
+                                   num_edges=num_edges)
+        prot.update(num_graphs=slots, max_nodes=self.max_len)
+        return prot
+
+    def _mol_dict(self, b, slots):
+        return dict(x=b["m_x"], edge_index=b["m_ei"], ntypes=b["m_nt"], etypes=b["m_et"], eattr=b["m_ea"], batch=b["m_batch"],
+                    num_graphs=slots, max_nodes=self.max_atoms)
+
+    # ---- bodies ---------------------------------------------------------------------------------------------------------
+    def _body_full(self, b, num_edges, slots):
+        pred, _ = self.model(self._protein_dict(b, num_edges, slots), self._mol_dict(b, slots))
+        return pred
+
+    def _body_embed(self, b, num_edges, slots):
+        from .joint import DenseIndex
+        prot = self._protein_dict(b, num_edges, slots)
+        hints = {k: prot.pop(k) for k in ("num_graphs", "max_nodes")}
+        embed = self.model.protein_gnn(**prot)
+        dense = DenseIndex(prot["batch"], embed.shape[0], device=embed.device, **hints)
+        return types.SimpleNamespace(embed=embed, batch=prot["batch"], dense=dense, slots=slots)
+
+    def _body_cached(self, h, b):
+        prot = dict(batch=h.batch, num_graphs=h.slots, max_nodes=self.max_len, protein_embed=h.embed, dense_index=h.dense)
+        pred, _ = self.model(prot, self._mol_dict(b, h.slots))
+        return pred
+
+    # ---- graph plumbing -----------------------------------------------------------------------------------------------------
+    def _run(self, key, keys, batch, fn):
+        """Replay (capturing on first use) `fn(static inputs)` for the bucket `key`."""
+        if self.launch_mode != "graph":
+            with torch.no_grad():
+                return fn(batch)
+        entry = self.graphs.get(key)
+        if entry is None:
+            static = {k: batch[k].to(self.dev, copy=True) for k in keys}
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(cur)
+            with torch.no_grad():
+                with torch.cuda.stream(side):
+                    for _ in range(self.capture_warmup):
+                        fn(static)
+                cur.wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                kw = {} if self.pool is None else {"pool": self.pool}
+                with torch.cuda.graph(graph, **kw):
+                    out = fn(static)
+            if self.pool is None:
+                self.pool = graph.pool()
+            entry = self.graphs[key] = types.SimpleNamespace(graph=graph, static=static, out=out)
+        for k in keys:
+            entry.static[k].copy_(batch[k], non_blocking=True)
+        entry.graph.replay()
+        return entry.out
+
+    def _check(self, meta):
+        if meta["max_len"] > self.max_len or meta["max_atoms"] > self.max_atoms:
+            raise ValueError(f"batch exceeds the step's bounds: longest protein {meta['max_len']} > {self.max_len} or "
+                             f"largest ligand {meta['max_atoms']} > {self.max_atoms}")
+
+    def predict(self, batch, meta):
+        """[slots, 1] standardised affinities (rows >= meta['pairs'] belong to the dummy pairs)."""
+        self._check(meta)
+        e = self._edges(meta)
+        key = ("full", meta["slots"], meta["n_pad"], e, meta["a_pad"], meta["me_pad"])
+        return self._run(key, self.PROT_KEYS + self.MOL_KEYS, batch, lambda b: self._body_full(b, e, meta["slots"]))
+
+    def embed_proteins(self, batch, meta):
+        self._check(meta)
+        e = self._edges(meta)
+        key = ("embed", meta["slots"], meta["n_pad"], e)
+        h = self._run(key, self.PROT_KEYS, batch, lambda b: self._body_embed(b, e, meta["slots"]))
+        h.key = key
+        return h
+
+    def predict_cached(self, handle, batch, meta):
+        self._check(meta)
+        key = ("cached", handle.key, meta["a_pad"], meta["me_pad"])
+        return self._run(key, self.MOL_KEYS, batch, lambda b: self._body_cached(handle, b))
+
+    def close(self):
+        self.graphs.clear()
+        self.pool = None

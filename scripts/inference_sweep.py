@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """BASELINE config 4: BindingDB-scale inference sweep, pairs sharded over the GPUs with no communication.
 
-    python scripts/inference_sweep.py --pairs 20000 [--graph dist4|knn30] [--ligands-per-protein 1]
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/inference_sweep.py ...
+    python scripts/inference_sweep.py --pairs 125000 [--graph knn30|dist4] [--ligands-per-protein 1] [--launch graph|eager]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/inference_sweep.py --pairs 1000000 ...
 
-Each rank takes pairs r, r+W, ... (caster_dta_b200.parallel.shard_pairs semantics), builds the residue graphs ON THE GPU
-from synthetic BindingDB-shape backbones (featurizer kernel, inside the timed region), runs CASTER-DTA(2,2) in eval mode
-through the public module API and keeps the predictions on the device.  A pool of distinct batches is cycled to stand in
-for the full pair list.  `--ligands-per-protein L > 1` enables the unique-protein embedding cache: the
-protein encoder runs once per protein batch and its residue embeddings are reused for the next L-1 ligand batches.
-Prints one JSON line (rank 0): pairs/s over all ranks (max-over-ranks device time).
+Each rank owns every W-th batch of the pair list (`parallel.shard_pairs` semantics, no collective in the data path).  Per
+batch, inside the timed region: H2D of the padded batch from pinned host memory (backbone coordinates, residue types, ligand
+graph), residue-graph featurizer on the device, graph-plan build, CASTER-DTA(2,2) forward in eval mode
+(`inference/evaluation.py:43-46`), predictions gathered on the device; one D2H of all predictions at the end.
+kNN graphs replay one CUDA graph per padded-shape bucket (`training.BucketedInferenceStep`); radius graphs have a
+data-dependent edge count and launch eagerly.  `--ligands-per-protein L > 1` enables the unique-protein embedding cache
+(SURVEY.md 8f N2): the protein side runs once per protein batch and its residue embeddings serve the next L ligand batches.
+A pool of distinct synthetic BindingDB-shape batches is cycled to stand in for the full pair list.
+Rank 0 checks the first batch's predictions against the CPU oracle and prints one JSON line.
 """
 import argparse
 import json
 import os
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -22,18 +26,53 @@ import torch
 import torch.distributed as dist
 
 import caster_dta_b200 as cg
-from caster_dta_b200 import synth
-from caster_dta_b200 import joint
+from caster_dta_b200 import loader, training
 from caster_dta_b200.configs import caster_dta_2_2
+
+
+def build_pool(args, rank):
+    """`pool` protein batches x L ligand batches each, padded and pinned.  Pair (i, j, k) = protein k of protein batch i with
+    ligand k of that batch's j-th ligand set."""
+    L, B = args.ligands_per_protein, args.batch
+    thresh, ttype = (4.0, "dist") if args.graph == "dist4" else (30, "num")
+    ds = loader.SyntheticPairDataset("bindingdb", args.pool * B * L, seed=1000 + rank, num_proteins=args.pool * B,
+                                     num_ligands=args.pool * B * L, edge_thresh=thresh, thresh_type=ttype)
+    ds.pairs = [(i * B + k, (i * L + j) * B + k) for i in range(args.pool) for j in range(L) for k in range(B)]
+    spec = loader.BucketSpec(B + 1, node_gran=1024)
+    out = []
+    for i in range(args.pool):
+        row = []
+        for j in range(L):
+            idx = list(range((i * L + j) * B, (i * L + j + 1) * B))
+            row.append(loader.pad_pairs(loader.collate_pairs(ds, idx), spec, pin=True))
+        out.append(row)
+    return ds, out, thresh, ttype
+
+
+def oracle_check(model, ds, t, m, thresh, ttype, pred):
+    from oracle import pipeline
+    from oracle import joint_oracle
+    kw = caster_dta_2_2()
+    p = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    n, a, me, pairs = m["nodes"], m["atoms"], m["mol_edges"], m["pairs"]
+    prot = pipeline.featurize_batch(t["coords"][:n].numpy(), t["ptr"][:pairs + 1].numpy(), t["idents"][:n].numpy(), ds.aa_table,
+                                    thresh, ttype, True, torch.float64)
+    mol = dict(x=t["m_x"][:a].double(), edge_index=t["m_ei"][:, :me], ntypes=t["m_nt"][:a], etypes=t["m_et"][:me],
+               eattr=t["m_ea"][:me].double(), batch=t["m_batch"][:a])
+    ref, _ = joint_oracle.joint_forward(p, kw, prot, mol)
+    err = float((pred.double().cpu() - ref.squeeze(-1)).abs().max() / ref.abs().max())
+    return {"pairs": pairs, "rel_err_vs_oracle": err, "tolerance": 1e-4, "ok": err <= 1e-4}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=20000, help="pairs in the whole sweep (all ranks)")
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--pool", type=int, default=16, help="distinct synthetic batches cycled per rank")
-    ap.add_argument("--graph", default="dist4", choices=["dist4", "knn30"])
+    ap.add_argument("--pool", type=int, default=8, help="distinct protein batches cycled per rank")
+    ap.add_argument("--graph", default="knn30", choices=["dist4", "knn30"])
     ap.add_argument("--ligands-per-protein", type=int, default=1)
+    ap.add_argument("--launch", default=None, choices=["graph", "eager"])
+    ap.add_argument("--no-oracle", action="store_true")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -44,68 +83,71 @@ def main():
     kw = caster_dta_2_2()
     torch.manual_seed(9)
     model = cg.JointGNN(kw["protein_gnn_kwargs"], kw["molecule_gnn_kwargs"], **kw["joint_gnn_kwargs"]).to(dev).eval()
-    thresh, ttype = (4.0, "dist") if args.graph == "dist4" else (30, "num")
-    pool = []
-    for b in range(args.pool):
-        pb = synth.protein_batch_coords("bindingdb", args.batch, 1000 * rank + b, self_avoiding=False)
-        mol = synth.molecule_batch(args.batch, 1000 * rank + b)
-        t = lambda a: torch.from_numpy(a).to(dev)
-        pool.append(dict(coords=t(pb["coords"]), ptr=t(pb["ptr"]), x_s=t(pb["x_s"]), x_v=t(pb["x_v"]), nt=t(pb["ntypes"]),
-                         batch=t(pb["batch"]), max_res=int(np.diff(pb["ptr"]).max()),
-                         mol={k: t(v) for k, v in mol.items()}, max_atoms=int(np.bincount(mol["batch"]).max())))
-    aa_table = torch.rand(20, 11, generator=torch.Generator().manual_seed(5)).to(dev)      # synthetic residue property table
-    my_batches = len(range(rank, args.pairs // args.batch, world))
-    preds, edges, residues = [], 0, 0
+    ds, pool, thresh, ttype = build_pool(args, rank)
+    launch = args.launch or ("graph" if ttype == "num" else "eager")
+    L, B = args.ligands_per_protein, args.batch
+    step = training.BucketedInferenceStep(model, torch.from_numpy(ds.aa_table), thresh, ttype, True, max_len=2048 + 32,
+                                          max_atoms=130, launch_mode=launch)
+    my_batches = len(range(rank, max(args.pairs // B, 1), world))
+    preds = torch.zeros(my_batches * B, device=dev)
+    stats = {"edges": 0, "residues": 0}
+
+    def to_dev(t):
+        return t if launch == "graph" else {k: v.to(dev, non_blocking=True) for k, v in t.items()}
 
     def run(nb, count):
-        nonlocal edges, residues
-        embed, dp, dense = None, None, None
-        for i in range(nb):
-            d = pool[i % len(pool)]
-            m = d["mol"]
-            molg = dict(x=m["x"], edge_index=m["edge_index"], ntypes=m["ntypes"], etypes=m["etypes"], eattr=m["eattr"],
-                        batch=m["batch"], num_graphs=args.batch, max_nodes=d["max_atoms"])
-            if embed is None or i % args.ligands_per_protein == 0:
-                dp = d                                   # the protein batch the next L ligand batches are paired with
-                # backbone coordinates -> node features -> residue graph -> encoder, all on the device
-                pgb = cg.protein_graph_batch(d["coords"], d["ptr"], d["nt"], aa_table, thresh, ttype, True)
-                ei = pgb["edge_index"]
-                embed = model.protein_gnn(**pgb)
-                dense = None
-                if count:
-                    edges += int(ei.shape[1]); residues += int(d["x_s"].shape[0])
-            if dense is None:
-                dense = joint.DenseIndex(dp["batch"], int(dp["batch"].shape[0]), num_graphs=args.batch, max_nodes=dp["max_res"])
-            prot = dict(batch=dp["batch"], num_graphs=args.batch, max_nodes=dp["max_res"], protein_embed=embed, dense_index=dense)
-            pred, _ = model(prot, molg)
+        handle = None
+        for s in range(nb):
+            i, j = (s // L) % len(pool), s % L
+            t, m = pool[i][j]
+            b = to_dev(t)
+            if L == 1:
+                out = step.predict(b, m)
+            else:
+                if j == 0 or handle is None:
+                    handle = step.embed_proteins(b, m)
+                out = step.predict_cached(handle, b, m)
             if count:
-                preds.append(pred)
+                preds[s * B: s * B + m["pairs"]].copy_(out[: m["pairs"], 0])
+                if j == 0:
+                    stats["residues"] += m["nodes"]
+                    stats["edges"] += step._edges(m) or 0
 
-    with torch.no_grad():
-        run(min(4, my_batches), False)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        run(my_batches, True)
-        b.record()
-        torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([my_batches * args.batch, edges, residues], dtype=torch.float64, device=dev)
+    warm = min(len(pool) * L, my_batches)
+    run(warm, False)                                           # captures every bucket of the pool
+    torch.cuda.synchronize()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    run(my_batches, True)
+    host = preds.cpu()                                         # D2H of every prediction
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([a.elapsed_time(b), wall * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([my_batches * B, stats["edges"], stats["residues"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt)
     if rank == 0:
-        ms = float(t.item())
-        print(json.dumps({"workload": f"CASTER-DTA(2,2) inference sweep, bindingdb-shape, graph {args.graph}, batch {args.batch}",
+        ms = float(tt[1])                                      # wall clock incl. H2D / D2H, max over ranks
+        check = None
+        if not args.no_oracle:
+            t, m = pool[0][0]
+            check = oracle_check(model, ds, t, m, thresh, ttype, host[: m["pairs"]])
+        print(json.dumps({"workload": f"CASTER-DTA(2,2) inference sweep, bindingdb-shape, graph {args.graph}, batch {B}",
                           "n_gpus": world, "pairs": int(cnt[0]), "ms": ms, "pairs_per_s": float(cnt[0]) / (ms * 1e-3),
-                          "protein_graphs_built": int(cnt[2]), "protein_edges": int(cnt[1]),
-                          "ligands_per_protein": args.ligands_per_protein,
-                          "finite": bool(torch.isfinite(torch.cat(preds)).all()),
-                          "note": "node + edge featurizer from backbone coordinates, encoder, cross-attention, head per batch; coordinates resident, no collective"}))
+                          "device_ms": float(tt[0]), "launch_mode": launch, "graphs_captured": len(step.graphs),
+                          "protein_residues_featurized": int(cnt[2]), "protein_edges": int(cnt[1]),
+                          "ligands_per_protein": L, "finite": bool(torch.isfinite(host).all()), "oracle_check": check,
+                          "note": "per batch: H2D from pinned host memory, node + edge featurizer from backbone coordinates, plan build, encoder, cross-attention, head; all predictions read back at the end; no collective"}))
+    step.close()
     if world > 1:
-        dist.destroy_process_group()
+        from caster_dta_b200 import parallel
+        if not parallel.shutdown():
+            os._exit(0)
 
 
 if __name__ == "__main__":
