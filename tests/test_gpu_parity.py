@@ -531,22 +531,31 @@ def test_fast_and_generic_kernels_agree_in_training_mode():
     f, gnr = res[True], res[False]
     assert_close(f[0], gnr[0].cpu(), TIGHT, "embedding", atol=1e-6)
 
-    def agree(a, b, what, atol):
+    def agree(a, b, what, atol, rows=True):
         """The two families sum s' of the first message GVP in different orders (per-node projections + edge part vs one
         pass over the concatenated input), so a pre-activation within round-off of zero can take the other ReLU branch in
-        one of them: that edge's whole term then differs.  Everything else must agree to round-off: >= 99.9 % of the
-        entries within TIGHT, and no entry further than 1e-3 of the tensor's scale."""
+        one of them: that edge's whole term then differs, and with it the gradient rows of that edge and of the nodes it
+        reaches -- a discontinuity of the function, not an arithmetic error (each family alone is within 4e-7 of the fp64
+        oracle on every conv output and gradient, scripts/dbg_conv.py).  Per-row tensors: at most 1 % of the rows may hold
+        an entry beyond TIGHT; parameter gradients are signed sums over all rows with heavy cancellation, so one flipped
+        term shows at up to ~1e-3 of a tensor's scale: each tensor within 1e-2, all of them together within 1e-3 (L2)."""
         a, b = a.detach().double().cpu(), b.detach().double().cpu()
         scale = float(b.abs().max())
         diff = (a - b).abs()
-        frac = float((diff <= TIGHT * scale + atol).double().mean())
-        assert frac >= 0.999, f"{what}: only {frac:.5f} of the entries agree to round-off"
-        assert float(diff.max()) <= 1e-3 * scale + atol, f"{what}: max diff {float(diff.max()):.3e} at scale {scale:.3e}"
+        if rows:
+            bad = (diff.reshape(diff.shape[0], -1) > TIGHT * scale + atol).any(dim=1)
+            assert float(bad.double().mean()) <= 0.01, f"{what}: {int(bad.sum())} of {bad.numel()} rows disagree beyond round-off"
+            assert float(diff.max()) <= scale + atol, f"{what}: max diff {float(diff.max()):.3e} at scale {scale:.3e}"
+        else:
+            assert float(diff.max()) <= 1e-2 * scale + atol, f"{what}: max diff {float(diff.max()):.3e} at scale {scale:.3e}"
 
     for i, what in enumerate(("embedding", "grad_x_s", "grad_x_v", "grad_e_s", "grad_e_v")):
         agree(f[i], gnr[i], what, 1e-6)
     for k in f[5]:
-        agree(f[5][k], gnr[5][k], "grad " + k, 1e-5)
+        agree(f[5][k], gnr[5][k], "grad " + k, 1e-5, rows=False)
+    fa = torch.cat([f[5][k].double().cpu().flatten() for k in f[5]])
+    fb = torch.cat([gnr[5][k].double().cpu().flatten() for k in f[5]])
+    assert float((fa - fb).norm() / fb.norm()) <= 1e-3, "parameter gradients (all tensors, L2-relative)"
 
 
 def test_conv_training_stash_is_bit_identical_to_recompute():
