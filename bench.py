@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--max-seconds", type=float, default=900.0, help="abort a run that takes longer than this (watchdog)")
     return ap.parse_args()
 
 
@@ -255,12 +256,32 @@ def reference_arm(args, world):
         "gpu_launches": 0})
 
 
+_T0 = time.time()
+
+
+def mark(rank, what):
+    """Progress marker on stderr (one line per stage and rank): a stuck run shows where it stopped."""
+    print(f"[bench rank {rank} +{time.time() - _T0:6.1f}s] {what}", file=sys.stderr, flush=True)
+
+
+def arm_watchdog(rank, seconds):
+    """A run that exceeds `seconds` (a hung collective, a stuck box) must not wait for the driver's kill: say so and leave."""
+    def fire():
+        print(f"[bench rank {rank}] watchdog: still running after {seconds} s -- aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     args = parse()
     quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    arm_watchdog(rank, args.max_seconds)
 
     if args.impl != "ours":
         if rank == 0:
@@ -282,7 +303,9 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
 
     # ---- data: this rank's shard of each global batch, padded to its bucket, pinned on the host and resident on the device --
+    mark(rank, "building the batch pool")
     ds, pool = build_pool(args.shape, args.pairs, args.pool, rank, world, pin=True)
+    mark(rank, f"pool ready: {[(m['nodes'], m['n_pad']) for _, m in pool]}")
     resident = [({k: v.to(dev) for k, v in t.items()}, m) for t, m in pool]
     h2d_bytes = [sum(v.numel() * v.element_size() for v in t.values()) for t, _ in pool]
     torch.cuda.synchronize()
@@ -303,6 +326,8 @@ def main():
     mk = dict(aa_table=torch.from_numpy(ds.aa_table), edge_thresh=KNN, thresh_type="num", keep_self_loops=True, max_len=max_len,
               max_atoms=128 + 2)
     graph_note = "eager launches (--no-graph)" if args.no_graph else "cuda graph per padded-shape bucket"
+    if world > 1 and not args.no_graph and os.environ.get("CGVP_ALLREDUCE_IN_GRAPH", "0") != "1":
+        graph_note += " (featurizer .. backward .. gradient pack); NCCL all-reduce + fused Adam launched after each replay"
     stepper = training.BucketedTrainStep(model, opt, launch_mode="eager" if args.no_graph else "graph", **mk)
     eager = training.BucketedTrainStep(model, opt, launch_mode="eager", **mk)
 
@@ -312,10 +337,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- setup (untimed): one eager step per bucket-distinct batch, then capture every bucket of the pool --------------------
+    mark(rank, "model ready; first eager step")
     l0 = _lib.LAUNCHES
     eager.step(*resident[0])
     launches_per_step = _lib.LAUNCHES - l0
     torch.cuda.synchronize()
+    mark(rank, "capturing the pool's buckets")
     if not args.no_graph:
         try:
             for b, m in resident:
@@ -326,7 +353,9 @@ def main():
             graph_note = f"eager launches (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
             stepper = eager
             torch.cuda.synchronize()
+    mark(rank, f"{len(getattr(stepper, 'graphs', {}))} graphs captured; barrier")
     barrier()
+    mark(rank, "warm-up")
 
     # ---- warm-up: exactly W steps of the timed kind -----------------------------------------------------------------------
     for i in range(args.warmup):
@@ -346,6 +375,7 @@ def main():
     # ---- timed region 1: device-resident pool --------------------------------------------------------------------------------
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     clocks = ClockSampler(local)
+    mark(rank, "timed region 1")
     barrier()
     if rank == 0:
         clocks.start()
@@ -373,6 +403,7 @@ def main():
 
     # per-kernel device time of the SAME steps: the library brackets each main kernel with CUDA events on the launching
     # stream; that needs host calls, so this pass launches eagerly (a graph replay makes none).  L2 flushed as above.
+    mark(rank, "per-kernel pass")
     _lib.profile_enable(True)
     edges_real = 0
     for i in range(args.steps):
@@ -410,6 +441,7 @@ def main():
     for s in range(2):
         done[s].record()
     e2e_steps = args.steps
+    mark(rank, "timed region 2 (e2e)")
     barrier()
     t0 = time.perf_counter()
     prefetch(0)
@@ -445,6 +477,7 @@ def main():
     else:
         e2e_value = float(t[1]) / float(t[0])
 
+    mark(rank, "gathering shapes")
     shapes = [(m["nodes"], KNN * m["nodes"], m["atoms"], m["n_pad"]) for _, m in pool]
     if world > 1:
         gathered = [None] * world

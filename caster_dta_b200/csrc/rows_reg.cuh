@@ -47,6 +47,9 @@ struct RowSpec {
                                          imax(PRE_NORM ? 1 + cdiv4(2 * S0) : 0, POST_NORM ? 1 + cdiv4(2 * OS) : 0));
     static constexpr int STG_FLOATS = STG_COLS * CGVP_WPITCH * 4;
     static constexpr int PER_WARP = PF + STG_FLOATS;
+    // training stash row: s' (pre-activation scalars) of GVP 0 [and GVP 1]
+    static constexpr int g1_so() { if constexpr (NG == 2) return G1::SO; else return 0; }
+    static constexpr int STASHF = pad4(G0::SO) + pad4(g1_so());
     static constexpr int bwd_warps() {
         for (int w = 16; w >= 4; w -= 4)
             if ((size_t)(WT + LNP + w * PER_WARP) * 4 + 1024 <= (size_t)CGVP_SMEM_OPTIN) return w;
@@ -92,10 +95,14 @@ struct RowFwd {
     LnStat st0, st1;
 };
 
-template <class S>
+// READ: the GVPs' s' come from the training stash (a.stash, written by an earlier forward over the same rows); otherwise they
+// are computed and, if a.stash is set and `store`, left there.
+template <class S, bool READ = false>
 __device__ __forceinline__ void rows_forward(const CgvpRowArgs& a, const float* wsm, int w1off, const float* lnp, long long row,
-                                             long long rin, RowFwd<S>& f, float (&os)[1][S::OS], float (&ov)[3][S::OV1]) {
+                                             long long rin, RowFwd<S>& f, float (&os)[1][S::OS], float (&ov)[3][S::OV1],
+                                             bool store = false) {
     using G0 = typename S::G0;
+    float* srow = a.stash ? a.stash + row * S::STASHF : nullptr;
     if constexpr (S::ONEHOT > 0) {
         const int ty = (int)__ldg(a.types + rin);
 #pragma unroll
@@ -143,11 +150,20 @@ __device__ __forceinline__ void rows_forward(const CgvpRowArgs& a, const float* 
     float ls[1][S::OS], lv[3][S::OV1];                                    // chain output
     if constexpr (S::NG == 1) {
         Save<G0> sv;
-        gvp_fwd<G0>(wsm, f.ys, f.yv, ls, lv, sv);
+        if constexpr (READ) { load_s<G0::SO, 0>(srow, 0, sv.sp); gvp_fwd<G0, 1>(wsm, f.ys, f.yv, ls, lv, sv); }
+        else { gvp_fwd<G0>(wsm, f.ys, f.yv, ls, lv, sv); if (store && srow) store_s<G0::SO, 0>(srow, 0, sv.sp, false); }
     } else {
         using G1 = typename S::G1;
-        { Save<G0> sv; gvp_fwd<G0>(wsm, f.ys, f.yv, f.cs, f.cv, sv); }
-        { Save<G1> sv; gvp_fwd<G1>(wsm + w1off, f.cs, f.cv, ls, lv, sv); }
+        {
+            Save<G0> sv;
+            if constexpr (READ) { load_s<G0::SO, 0>(srow, 0, sv.sp); gvp_fwd<G0, 1>(wsm, f.ys, f.yv, f.cs, f.cv, sv); }
+            else { gvp_fwd<G0>(wsm, f.ys, f.yv, f.cs, f.cv, sv); if (store && srow) store_s<G0::SO, 0>(srow, 0, sv.sp, false); }
+        }
+        {
+            Save<G1> sv;
+            if constexpr (READ) { load_s<G1::SO, 0>(srow + pad4(G0::SO), 0, sv.sp); gvp_fwd<G1, 1>(wsm + w1off, f.cs, f.cv, ls, lv, sv); }
+            else { gvp_fwd<G1>(wsm + w1off, f.cs, f.cv, ls, lv, sv); if (store && srow) store_s<G1::SO, 0>(srow + pad4(G0::SO), 0, sv.sp, false); }
+        }
     }
     if constexpr (S::POST_RES) {                                          // x1 + D1(ff(x1)), gvp_layers.py:410
         if (a.mask1_s) {
@@ -209,13 +225,13 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_reg_kernel(const __grid_const
         const long long rin = A.a.in_index ? (long long)__ldg(A.a.in_index + row) : row;
         RowFwd<S> f;
         float os[1][S::OS], ov[3][S::OV1];
-        rows_forward<S>(A.a, wsm, S::WF1, lnp, row, rin, f, os, ov);
+        rows_forward<S>(A.a, wsm, S::WF1, lnp, row, rin, f, os, ov, true);
         store_s<S::OS, 0>(A.a.out_s, row, os, false);
         if constexpr (S::OV > 0) store_v<S::OV, 0>(A.a.out_v, row, ov, false);
     }
 }
 
-template <class S>
+template <class S, bool READ>
 __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __grid_constant__ RowsRegArgs A) {
     using G0 = typename S::G0;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -242,8 +258,9 @@ __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __gri
         float gs[1][S::OS], gv[3][S::OV1];                                // gradient wrt the chain output
         {
             float os[1][S::OS], ov[3][S::OV1];
-            rows_forward<S>(A.a, wsm, S::WT1, lnp, row, rin, f, os, ov);
+            rows_forward<S, READ>(A.a, wsm, S::WT1, lnp, row, rin, f, os, ov);
         }
+        const float* srow = READ ? A.a.stash + row * S::STASHF : nullptr;
         float dfs[1][S::OS], dfv[3][S::OV1];                              // gradient wrt the pre-LayerNorm1 tensor
         {
             float gys[1][S::OS], gyv[3][S::OV1];
@@ -296,7 +313,8 @@ __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __gri
             {
                 Save<G1> sv;
                 float so[1][G1::SO], vo[3][G1::VO1], dsin[1][G1::KSD], dvin[3][G1::VI1];
-                gvp_fwd<G1>(wsm + S::WT1, f.cs, f.cv, so, vo, sv);
+                if constexpr (READ) { load_s<G1::SO, 0>(srow + pad4(G0::SO), 0, sv.sp); gvp_fwd<G1, 1>(wsm + S::WT1, f.cs, f.cv, so, vo, sv); }
+                else gvp_fwd<G1>(wsm + S::WT1, f.cs, f.cv, so, vo, sv);
                 gvp_bwd<G1>(wsm + S::WT1, sv, f.cs, f.cv, gs, gv, sink, S::GO1, dsin, dvin);
 #pragma unroll
                 for (int c = 0; c < G1::SI; ++c) g1s[0][c] = dsin[0][c];
@@ -307,7 +325,8 @@ __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __gri
             }
             Save<G0> sv;
             float so[1][G0::SO], vo[3][G0::VO1], dsin[1][G0::KSD], dvin[3][G0::VI1];
-            gvp_fwd<G0>(wsm, f.ys, f.yv, so, vo, sv);
+            if constexpr (READ) { load_s<G0::SO, 0>(srow, 0, sv.sp); gvp_fwd<G0, 1>(wsm, f.ys, f.yv, so, vo, sv); }
+            else gvp_fwd<G0>(wsm, f.ys, f.yv, so, vo, sv);
             gvp_bwd<G0>(wsm, sv, f.ys, f.yv, g1s, g1v, sink, S::GO0, dsin, dvin);
 #pragma unroll
             for (int c = 0; c < S::S0; ++c) dys[0][c] = dsin[0][c];
@@ -318,7 +337,8 @@ __global__ void __launch_bounds__(S::BW * 32, 1) rows_bwd_reg_kernel(const __gri
         } else {
             Save<G0> sv;
             float so[1][G0::SO], vo[3][G0::VO1], dsin[1][G0::KSD], dvin[3][G0::VI1];
-            gvp_fwd<G0>(wsm, f.ys, f.yv, so, vo, sv);
+            if constexpr (READ) { load_s<G0::SO, 0>(srow, 0, sv.sp); gvp_fwd<G0, 1>(wsm, f.ys, f.yv, so, vo, sv); }
+            else gvp_fwd<G0>(wsm, f.ys, f.yv, so, vo, sv);
             // an embed of leaf features (no residual, no pre-norm, nobody asks for d_in) needs weight gradients only
             if (S::PRE_NORM || S::POST_RES || S::RES_IN || A.g.d_in_s || A.g.d_in_v)
                 gvp_bwd<G0>(wsm, sv, f.ys, f.yv, gs, gv, sink, S::GO0, dsin, dvin);
@@ -418,6 +438,7 @@ static int launch_fwd(const CgvpRowArgs* args, cudaStream_t st) {
     A.wp[0] = args->h_packed[0];
     if (S::NG == 2) A.wp[1] = args->h_packed[1];
     A.ntiles = (int)cdiv64(args->rows, 32);
+    if (A.a.stash && !aligned16(A.a.stash)) A.a.stash = nullptr;
     const int sms = cgvp_num_sms();
     const int grid = (int)min((long long)cdiv(A.ntiles, 8), (long long)sms * 2);
     const size_t smem = S::smem_fwd();
@@ -447,9 +468,13 @@ static int launch_bwd(const CgvpRowArgs* args, const CgvpRowGradArgs* grads, voi
     A.partial = reinterpret_cast<float*>(ws);
     float* reduced = A.partial + (int64_t)grid * S::PF;
     const size_t smem = S::smem_bwd();
-    CGVP_CUDA(cudaFuncSetAttribute(rows_bwd_reg_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool read = args->stash != nullptr && aligned16(args->stash);
+    if (!read) A.a.stash = nullptr;
+    if (read) CGVP_CUDA(cudaFuncSetAttribute(rows_bwd_reg_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CGVP_CUDA(cudaFuncSetAttribute(rows_bwd_reg_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cgvp_prof_begin(CGVP_K_ROWS_BWD, st);
-    rows_bwd_reg_kernel<S><<<grid, S::BW * 32, smem, st>>>(A);
+    if (read) rows_bwd_reg_kernel<S, true><<<grid, S::BW * 32, smem, st>>>(A);
+    else rows_bwd_reg_kernel<S, false><<<grid, S::BW * 32, smem, st>>>(A);
     cgvp_prof_end(CGVP_K_ROWS_BWD, st);
     CGVP_LAUNCH_CHECK("rows_bwd_reg_kernel");
     CgvpSeg seg[CGVP_MAX_SEGS];
@@ -487,4 +512,5 @@ static bool try_bwd(const CgvpRowDesc* d, const CgvpRowArgs* a, const CgvpRowGra
     bool rows_try_fwd_##NAME(const CgvpRowDesc* d, const CgvpRowArgs* a, cudaStream_t st, int* rc) { return try_fwd<SPEC>(d, a, st, rc); } \
     bool rows_try_bwd_##NAME(const CgvpRowDesc* d, const CgvpRowArgs* a, const CgvpRowGradArgs* g, void* ws, int64_t wsb,   \
                              cudaStream_t st, int* rc) { return try_bwd<SPEC>(d, a, g, ws, wsb, st, rc); }                   \
-    int rows_pf_##NAME(const CgvpRowDesc* d) { return SPEC::matches(*d) ? SPEC::PF : 0; }
+    int rows_pf_##NAME(const CgvpRowDesc* d) { return SPEC::matches(*d) ? SPEC::PF : 0; }                                    \
+    int rows_stashf_##NAME(const CgvpRowDesc* d) { return SPEC::matches(*d) ? SPEC::STASHF : 0; }

@@ -44,7 +44,7 @@ class SyntheticPairDataset:
         lens = synth.protein_lengths(shape, num_proteins, rng)
         self.proteins = []
         for n in lens:
-            c = synth.random_backbone(int(n), rng, self_avoiding)
+            c = synth.random_backbone(int(n), rng, True) if self_avoiding else synth.random_backbone_fast(int(n), rng)
             self.proteins.append(dict(coords=c, idents=rng.integers(0, synth.NUM_RESIDUE_TYPES, size=int(n)).astype(np.int64)))
         self.ligands = [synth.random_molecule(rng) for _ in range(num_ligands)]
         if num_proteins == num_pairs and num_ligands == num_pairs:
@@ -126,7 +126,7 @@ def _filler_backbone(n):
     have = _FILLER.get("coords")
     if have is None or have.shape[0] < n:
         rng = np.random.default_rng(424242)
-        have = synth.random_backbone(max(n, 4096), rng)
+        have = synth.random_backbone_fast(max(n, 4096), rng)
         _FILLER["coords"] = have
         _FILLER["idents"] = rng.integers(0, synth.NUM_RESIDUE_TYPES, size=have.shape[0]).astype(np.int64)
     return have[:n], _FILLER["idents"][:n]

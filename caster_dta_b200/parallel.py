@@ -160,6 +160,11 @@ class FlatAdam:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return self.flat_grad
 
+    def all_reduce(self):
+        """The collective alone (sum of the packed flat gradient over the ranks)."""
+        if self.world() > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
     def step(self):
         self.master.grad = self.flat_grad
         self.opt.step()

@@ -51,6 +51,22 @@ def random_backbone(n, rng, self_avoiding=False, min_sep=4.5):
     return out.astype(np.float32)
 
 
+def random_backbone_fast(n, rng):
+    """Vectorised `random_backbone(n, rng, self_avoiding=False)`: the same chain model (3.8 A C-alpha steps in uniformly
+    random directions, Gaussian offsets for N / C / O) drawn with array calls -- a different random stream, so the loader's
+    data sets use this one and the committed fixtures keep the step-by-step generator."""
+    step = rng.normal(size=(n, 3))
+    step /= np.linalg.norm(step, axis=1, keepdims=True)
+    step[0] = 0.0
+    ca = np.cumsum(CA_STEP * step, axis=0)
+    out = np.empty((n, 4, 3), dtype=np.float64)
+    out[:, 1] = ca
+    out[:, 0] = ca + rng.normal(scale=0.8, size=(n, 3))
+    out[:, 2] = ca + rng.normal(scale=0.8, size=(n, 3))
+    out[:, 3] = ca + rng.normal(scale=1.2, size=(n, 3))
+    return out.astype(np.float32)
+
+
 def _safe_unit(x):
     nrm = np.sqrt((x * x).sum(-1, keepdims=True))
     return np.where(nrm > 0, x / np.where(nrm > 0, nrm, 1), 0.0)

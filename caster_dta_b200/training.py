@@ -12,6 +12,7 @@ work -- nothing is cached across batches:
 A replay after copying another batch of the same bucket into the static input buffers therefore computes that batch's
 step (`tests/test_gpu_parity.py::test_bucketed_graph_step_matches_oracle_on_two_batches`).
 """
+import os
 import types
 
 import torch
@@ -36,7 +37,8 @@ class BucketedTrainStep:
     pool); "eager": the same work launched kernel by kernel."""
 
     def __init__(self, model, flat_adam, aa_table, edge_thresh=30, thresh_type="num", keep_self_loops=True,
-                 max_len=1056, max_atoms=128, launch_mode="graph", update=True, capture_warmup=2, record_masks=False):
+                 max_len=1056, max_atoms=128, launch_mode="graph", update=True, capture_warmup=2, record_masks=False,
+                 collective_in_graph=None):
         if thresh_type not in ("num", "prop"):
             raise ValueError("fixed-shape steps need an edge count known on the host: 'num' or 'prop' graphs")
         self.model, self.opt = model, flat_adam
@@ -50,6 +52,14 @@ class BucketedTrainStep:
         self.pool = None
         self.record_masks = record_masks      # parity tests: every dropout site leaves its mask (ops.MASK_LOG)
         self.last_masks = None
+        # Where the all-reduce (and the Adam kernel after it) run when there is more than one rank:
+        #   inside each bucket's graph  -- validated on 2 GPUs (tests/test_gpu_multi.py); with 8 ranks whose pools hold different
+        #                                  bucket sets the captured-collective path hung on this box (round 2), so it is opt-in
+        #                                  (CGVP_ALLREDUCE_IN_GRAPH=1);
+        #   eagerly after the replay    -- default for N > 1: one NCCL launch + one fused Adam launch per step outside the graph.
+        if collective_in_graph is None:
+            collective_in_graph = flat_adam.world() == 1 or os.environ.get("CGVP_ALLREDUCE_IN_GRAPH", "0") == "1"
+        self.collective_in_graph = bool(collective_in_graph)
 
     # ---- the work of one step on the tensors of `b` -------------------------------------------------------------------
     def body(self, b, num_edges, slots, warm=False):
@@ -66,8 +76,9 @@ class BucketedTrainStep:
         self.opt.reset()
         loss.backward()
         ops.join_wgrad_stream()
-        self.opt.sync(collective=not warm)
-        if self.update and not warm:
+        tail = self.collective_in_graph or self.launch_mode != "graph"       # the collective + Adam belong to this body
+        self.opt.sync(collective=tail and not warm)
+        if self.update and tail and not warm:
             self.opt.step()
         return loss.detach(), pred.detach()
 
@@ -103,6 +114,10 @@ class BucketedTrainStep:
         for k in INPUT_KEYS:
             entry.static[k].copy_(batch[k], non_blocking=True)
         entry.graph.replay()
+        if not self.collective_in_graph:          # N > 1 default: the collective and the fused Adam kernel follow the replay
+            self.opt.all_reduce()
+            if self.update:
+                self.opt.step()
         self.last_pred, self.last_masks = entry.pred, entry.masks
         return entry.loss
 

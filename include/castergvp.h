@@ -196,6 +196,9 @@ typedef struct CgvpRowArgs {
     const float *ln0_w, *ln0_b, *ln1_w, *ln1_b;
     const float* const* h_packed;      /* host array of n_gvp device pointers */
     float *out_s, *out_v;
+    float* stash;                      /* optional training stash [rows, cgvp_rows_stash_floats(desc)]: the forward leaves the
+                                          pre-activation scalars s' of its GVPs, the backward (same pointer) then skips every
+                                          W_s projection of its recompute; NULL = recompute */
 } CgvpRowArgs;
 
 typedef struct CgvpRowGradArgs {
@@ -207,6 +210,8 @@ typedef struct CgvpRowGradArgs {
 } CgvpRowGradArgs;
 
 int64_t cgvp_rows_workspace_bytes(const CgvpRowDesc* desc, int64_t rows, int32_t backward);
+/* floats per row of the training stash, 0 if the kernels serving `desc` keep none */
+int64_t cgvp_rows_stash_floats(const CgvpRowDesc* desc);
 int32_t cgvp_rows_fwd(const CgvpRowDesc* desc, const CgvpRowArgs* args, void* ws, int64_t ws_bytes,
                       cgvp_stream_t stream);
 int32_t cgvp_rows_bwd(const CgvpRowDesc* desc, const CgvpRowArgs* args, const CgvpRowGradArgs* grads, void* ws,

@@ -2,8 +2,9 @@
 `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
 
 SURVEY.md 8(e) / 4(v): (1) the all-reduced gradient of a global batch sharded over two ranks equals the single-process
-gradient of the whole batch; (2) after real training steps (dropout on, every rank its own masks, the all-reduce captured
-inside each rank's CUDA graph) the replicas hold bit-identical weights.
+gradient of the whole batch (all-reduce launched after the graph replay, the default for N > 1); (2) after real training
+steps (dropout on, every rank its own masks, the all-reduce AND Adam captured inside each rank's CUDA graph) the replicas hold
+bit-identical weights.
 """
 import os
 import sys
@@ -64,7 +65,7 @@ def _worker(rank, world, port, out):
             out["grad_rel_err"] = err
         # ---- (2) replicas stay bit-identical through real steps (train mode, dropout, captured all-reduce + Adam) ---------------
         model.train()
-        tstep = training.BucketedTrainStep(model, opt, table, launch_mode="graph", update=True, **mk)
+        tstep = training.BucketedTrainStep(model, opt, table, launch_mode="graph", update=True, collective_in_graph=True, **mk)
         for t, m in mine[:4]:
             tstep.step({k: v.to(dev) for k, v in t.items()}, m)
         torch.cuda.synchronize()
