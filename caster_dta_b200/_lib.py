@@ -50,7 +50,7 @@ class RowDesc(C.Structure):
 class RowArgs(C.Structure):
     _fields_ = [("rows", C.c_int64)] + [(n, C.c_void_p) for n in (
         "in_s", "in_v", "types", "in_index", "h_s", "h_v", "mask0_s", "mask0_v", "mask1_s", "mask1_v",
-        "ln0_w", "ln0_b", "ln1_w", "ln1_b", "h_packed", "out_s", "out_v")]
+        "ln0_w", "ln0_b", "ln1_w", "ln1_b", "h_packed", "out_s", "out_v", "stash")]
 
 
 class RowGradArgs(C.Structure):
@@ -94,6 +94,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cgvp_rows_workspace_bytes": (C.c_int64, [C.POINTER(RowDesc), C.c_int64, C.c_int32]),
+    "cgvp_rows_stash_floats": (C.c_int64, [C.POINTER(RowDesc)]),
     "cgvp_rows_fwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.c_void_p, C.c_int64, C.c_void_p]),
     "cgvp_rows_bwd": (C.c_int32, [C.POINTER(RowDesc), C.POINTER(RowArgs), C.POINTER(RowGradArgs), C.c_void_p,
                                   C.c_int64, C.c_void_p]),

@@ -412,6 +412,12 @@ static int choose_geometry(RowsK& K, int smem_max, size_t* smem_bytes) {
     return -1;
 }
 
+int rows_special_stash_floats(const CgvpRowDesc* desc);
+extern "C" int64_t cgvp_rows_stash_floats(const CgvpRowDesc* desc) {
+    if (!desc) return 0;
+    return rows_special_stash_floats(desc);
+}
+
 extern "C" int64_t cgvp_rows_workspace_bytes(const CgvpRowDesc* desc, int64_t rows, int32_t backward) {
     if (!backward) return 16 + rows_wide_workspace_bytes(desc, rows);
     RowsK K;

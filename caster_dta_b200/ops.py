@@ -211,7 +211,7 @@ def _row_args(prog, rows, t, arena, offs):
     a = _lib.RowArgs()
     a.rows = rows
     for name in ("in_s", "in_v", "types", "in_index", "h_s", "h_v", "mask0_s", "mask0_v", "mask1_s", "mask1_v",
-                 "ln0_w", "ln0_b", "ln1_w", "ln1_b", "out_s", "out_v"):
+                 "ln0_w", "ln0_b", "ln1_w", "ln1_b", "out_s", "out_v", "stash"):
         v = t.get(name)
         setattr(a, name, None if v is None else v.data_ptr())
     blocks = (C.c_void_p * max(len(offs), 1))(*[arena.data_ptr() + 4 * o for o in offs])
@@ -236,6 +236,12 @@ class RowsFunction(torch.autograd.Function):
         arena, offs = pack_weights(prog.gvps, weights, dev)
         t["out_s"] = torch.empty(rows, prog.out_s, dtype=torch.float32, device=dev)
         t["out_v"] = torch.empty(rows, prog.out_v, 3, dtype=torch.float32, device=dev)
+        # training: the specialised kernels leave the GVPs' pre-activation scalars per row for the backward (USE_ROWS_STASH)
+        t["stash"] = None
+        if USE_ROWS_STASH and any(ctx.needs_input_grad) and rows > 0:
+            sf = int(lib().cgvp_rows_stash_floats(C.byref(prog.desc)))
+            if sf > 0:
+                t["stash"] = torch.empty(rows, sf, dtype=torch.float32, device=dev)
         a, blocks = _row_args(prog, rows, t, arena, offs)
         nbytes = lib().cgvp_rows_workspace_bytes(C.byref(prog.desc), rows, 0)
         ws = _workspace(nbytes, dev)
@@ -322,6 +328,7 @@ class ConvProgram:
 
 
 USE_CONV_STASH = True    # forward stash for the conv backward (cgvp_conv_fwd_stash / cgvp_conv_bwd_stash)
+USE_ROWS_STASH = True    # forward stash of the row programs (CgvpRowArgs.stash): the backward skips the W_s recompute
 
 
 class ConvFunction(torch.autograd.Function):
