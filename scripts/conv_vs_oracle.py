@@ -1,5 +1,9 @@
+"""Per-tensor errors of the fused GVPConv (both kernel families) against the fp64 oracle: outputs, input / edge-attribute
+gradients and every parameter gradient, on hub / ragged random graphs.  `python scripts/conv_vs_oracle.py` on a B200."""
 import sys, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch.nn.functional as F
 import caster_dta_b200 as cg
 from caster_dta_b200 import _lib

@@ -3,8 +3,10 @@
 //   const : __constant__ bank, LDCU.128 into uniform registers, FFMA2 with a UR operand (no shared-memory crossbar
 //           traffic, no vector registers for weights)
 // Work: the full forward of message GVP 0 at checkpoint dims (64,9)->(16,4), h=9, per row (1 583 FMA), ITER rows per thread.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I caster_dta_b200/csrc \
-//        scripts/microbench/weights_src.cu caster_dta_b200/csrc/pack.o? (header only) -o /tmp/wsrc
+// Build (from the repo root; header-only dependency on cgvp_reg.cuh):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I caster_dta_b200/csrc \
+//        scripts/microbench/weights_src.cu -o scripts/microbench/weights_src
+// Result on a B200: profiles/r2_weights_src_microbench.jsonl
 #include <cstdio>
 #include <vector>
 #include "cgvp_reg.cuh"

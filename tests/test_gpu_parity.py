@@ -536,7 +536,7 @@ def test_fast_and_generic_kernels_agree_in_training_mode():
         pass over the concatenated input), so a pre-activation within round-off of zero can take the other ReLU branch in
         one of them: that edge's whole term then differs, and with it the gradient rows of that edge and of the nodes it
         reaches -- a discontinuity of the function, not an arithmetic error (each family alone is within 4e-7 of the fp64
-        oracle on every conv output and gradient, scripts/dbg_conv.py).  Per-row tensors: at most 1 % of the rows may hold
+        oracle on every conv output and gradient, scripts/conv_vs_oracle.py).  Per-row tensors: at most 1 % of the rows may hold
         an entry beyond TIGHT; parameter gradients are signed sums over all rows with heavy cancellation, so one flipped
         term shows at up to ~1e-3 of a tensor's scale: each tensor within 1e-2, all of them together within 1e-3 (L2)."""
         a, b = a.detach().double().cpu(), b.detach().double().cpu()
