@@ -135,9 +135,15 @@ def set_fast_paths(on):
     lib().cgvp_set_fast_paths(int(bool(on)))
 
 
+TENSOR_CORES = False   # mirror of the library's precision mode for the host-side paths (caster_dta_b200/wide.py)
+
+
 def set_tensor_cores(on):
-    """0 (default): fp32 everywhere; 1: tcgen05 bf16 message GEMMs where compiled in (<= 1e-2 of the reference)."""
+    """0 (default): fp32 everywhere; 1: tcgen05 bf16 message GEMMs where compiled in, TF32 library GEMMs in the
+    wide-dims GEMM formulation (<= 1e-2 of the reference)."""
+    global TENSOR_CORES
     lib().cgvp_set_tensor_cores(int(bool(on)))
+    TENSOR_CORES = bool(on)
 
 
 def profile_enable(on):

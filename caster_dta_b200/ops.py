@@ -9,7 +9,7 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, wide
 from ._lib import lib, check
 
 
@@ -259,6 +259,12 @@ class RowsFunction(torch.autograd.Function):
         prog, t, rows = ctx.prog, dict(ctx.t), ctx.rows
         dev = t["in_s"].device
         need = ctx.needs_input_grad
+        if rows > 0 and wide.rows_supported(prog, t):
+            # wide dims (config 5): the backward as a short sequence of library GEMMs (wide.py) instead of the generic tile kernel
+            r = wide.rows_backward(prog, t, [_f32(w) for w in ctx.weights], _f32(d_out_s), _f32(d_out_v) if prog.out_v else None)
+            want_h = prog.residual_in and (need[5] or need[6])
+            return (None, r["d_in_s"] if need[1] else None, r["d_in_v"] if (need[2] and prog.in_v) else None, None, None,
+                    r["d_h_s"] if want_h else None, r["d_h_v"] if want_h else None, None, None, None, None, *r["ln"], *r["dw"])
         g = _lib.RowGradArgs()
         d_out_s = _f32(d_out_s)
         d_out_v = _f32(d_out_v) if prog.out_v else None
@@ -338,6 +344,15 @@ class ConvFunction(torch.autograd.Function):
     def forward(ctx, prog, plan, x_s, x_v, e_s, e_v, *weights):
         dev = x_s.device
         x_s, x_v, e_s, e_v = _f32(x_s), _f32(x_v), _f32(e_s), _f32(e_v)
+        ctx.prog, ctx.plan, ctx.saved, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), weights
+        ctx.wide = wide.conv_supported(prog)
+        if ctx.wide and not _lib.TENSOR_CORES:
+            # wide dims (config 5), fp32 mode: chunked GEMM formulation (wide.py); the tensor-core mode keeps the fused
+            # tcgen05 forward (csrc/conv_tc.cu) and shares the backward below
+            out_s, out_v = wide.conv_forward(prog, plan, x_s, x_v, e_s, e_v, [_f32(w) for w in weights])
+            ctx.stash = ctx.arena = ctx.offs = None
+            ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
+            return out_s, out_v
         arena, offs = pack_weights(prog.gvps, weights, dev)
         out_s = torch.empty(plan.N, prog.out_s, dtype=torch.float32, device=dev)
         out_v = torch.empty(plan.N, prog.out_v, 3, dtype=torch.float32, device=dev)
@@ -353,8 +368,7 @@ class ConvFunction(torch.autograd.Function):
                 stash = torch.empty(sbytes, dtype=torch.uint8, device=dev)
         _lib.timed_call("cgvp_conv_fwd", lib().cgvp_conv_fwd_stash, C.byref(prog.desc), C.byref(plan.c), _ptr(x_s), _ptr(x_v), _ptr(e_s),
                         _ptr(e_v), blocks, _ptr(out_s), _ptr(out_v), wp, wn, _ptr(stash), _stream())
-        ctx.stash = stash
-        ctx.prog, ctx.plan, ctx.saved, ctx.arena, ctx.offs, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), arena, offs, weights
+        ctx.stash, ctx.arena, ctx.offs = stash, arena, offs
         ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
         return out_s, out_v
 
@@ -364,6 +378,10 @@ class ConvFunction(torch.autograd.Function):
         x_s, x_v, e_s, e_v = ctx.saved
         dev = x_s.device
         d_out_s, d_out_v = _f32(d_out_s), _f32(d_out_v)
+        if ctx.wide:
+            d_x_s, d_x_v, d_e_s, d_e_v, dw = wide.conv_backward(prog, plan, x_s, x_v, e_s, e_v, [_f32(w) for w in ctx.weights],
+                                                                d_out_s, d_out_v)
+            return (None, None, d_x_s, d_x_v, d_e_s, d_e_v, *dw)
         d_x_s, d_x_v = torch.empty_like(x_s), torch.empty_like(x_v)
         d_e_s, d_e_v = torch.empty_like(e_s), torch.empty_like(e_v)
         total = sum((sp.packed_floats() + 3) // 4 * 4 for sp in prog.gvps)

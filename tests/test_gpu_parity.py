@@ -21,6 +21,17 @@ def _mods():
     return cg
 
 
+@pytest.fixture(autouse=True)
+def _c_abi_kernels_only():
+    """This file pins the kernels of libcastergvp.so: wide descriptors stay on the tile / tcgen05 kernels here; their GEMM
+    formulation (`caster_dta_b200/wide.py`) has its own file, tests/test_gpu_wide.py."""
+    from caster_dta_b200 import wide
+    prev = wide.ENABLED
+    wide.set_enabled(False)
+    yield
+    wide.set_enabled(prev)
+
+
 @pytest.fixture(params=["fast", "generic"])
 def kernel_path(request):
     """Run a test once with the specialised register-resident kernels (where compiled in) and once with the
