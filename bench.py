@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-config5", action="store_true", help="skip the isolated GVPConvLayer (100,16)/(32,1) measurement")
     ap.add_argument("--max-seconds", type=float, default=900.0, help="abort a run that takes longer than this (watchdog)")
     return ap.parse_args()
 
@@ -254,6 +255,91 @@ def reference_arm(args, world):
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
+
+
+def config5_block(dev, edges=1_000_000, iters=5):
+    """BASELINE config 5 beside the headline (rank 0, N = 1): one isolated `GVPConvLayer` at nodes (100,16) / edges (32,1),
+    `vector_gate=True, activations=(ReLU, None), aggr='mean', drop_rate=0` on the synthetic chain-kNN graph of SURVEY.md 8(d),
+    E = 1 M: forward and forward+backward per precision mode, CUDA events, and a parity line (GEMM formulation vs the generic
+    tile kernels of the same library at E = 60 k).  Never raises: the headline line must not depend on it."""
+    import torch.nn.functional as F
+    import caster_dta_b200 as cg
+    from caster_dta_b200 import _lib, synth, wide
+    res = {"dims": "nodes (100,16), edges (32,1)", "flops_per_edge_fwd": 132820}
+    prev_wide = wide.ENABLED
+    try:
+        nd, ed = (100, 16), (32, 1)
+
+        def make(num_edges):
+            ei_np, n = synth.conv_microbench_graph(num_edges, 30)
+            ei = torch.from_numpy(ei_np).to(dev)
+            g = torch.Generator(device=dev).manual_seed(9)
+            r = lambda *sh: torch.randn(*sh, generator=g, device=dev)
+            e = ei.shape[1]
+            return ei, n, e, [r(n, nd[0]), r(n, nd[1], 3), r(e, ed[0]), r(e, ed[1], 3)]
+
+        torch.manual_seed(9)
+        layer = cg.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean").to(dev).train()
+
+        def run(ei, data, backward):
+            leaves = [t.detach().requires_grad_(backward) for t in data]
+            layer.zero_grad(set_to_none=True)
+            with torch.set_grad_enabled(backward):
+                out = layer((leaves[0], leaves[1]), ei, (leaves[2], leaves[3]))
+                if backward:
+                    (out[0].square().sum() + out[1].square().sum()).backward()
+            return out, leaves
+
+        def timed(ei, data, backward, n_it):
+            for _ in range(2):
+                run(ei, data, backward)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(n_it):
+                run(ei, data, backward)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n_it
+
+        ei, n, e, data = make(edges)
+        res["nodes"], res["edges"] = n, e
+        modes = {}
+        for name, gemm, tc, bwd in (("fwd_tcgen05_bf16", True, True, False), ("fwd_fp32_gemm", True, False, False),
+                                    ("fwd_bwd_fp32_gemm", True, False, True), ("fwd_bwd_tcgen05_fwd_tf32_bwd", True, True, True)):
+            wide.set_enabled(gemm)
+            _lib.set_tensor_cores(tc)
+            try:
+                ms = timed(ei, data, bwd, iters)
+                modes[name] = {"ms": ms, "edges_per_s": e / (ms * 1e-3),
+                               "algorithmic_tflops": 132820.0 * (3 if bwd else 1) * e / (ms * 1e-3) / 1e12}
+            except Exception as exc:                                   # noqa: BLE001
+                modes[name] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+            finally:
+                _lib.set_tensor_cores(False)
+        res["modes"] = modes
+        del ei, data
+        # the generic tile kernels (the only training path of these dims before wide.py), on a graph they finish quickly
+        ei, n, e, data = make(60_000)
+        small = {"edges": e}
+        grads = {}
+        for name, gemm in (("gemm", True), ("tile", False)):
+            wide.set_enabled(gemm)
+            small[name + "_fwd_bwd_ms"] = timed(ei, data, True, 3)
+            out, leaves = run(ei, data, True)
+            grads[name] = [out[0].detach(), out[1].detach()] + [t.grad for t in leaves] + [q.grad.clone() for q in layer.parameters() if q.numel()]
+        worst = 0.0
+        for a, b in zip(grads["gemm"], grads["tile"]):
+            worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp(min=1e-30)))
+        small["max_scale_relative_difference_gemm_vs_tile"] = worst
+        small["tile_ms_per_1M_edges_extrapolated"] = small["tile_fwd_bwd_ms"] * 1e6 / e
+        res["tile_kernels_reference"] = small
+    except Exception as exc:                                           # noqa: BLE001
+        res["error"] = f"{type(exc).__name__}: {str(exc)[:200]}"
+    finally:
+        wide.set_enabled(prev_wide)
+        _lib.set_tensor_cores(False)
+    return res
 
 
 _T0 = time.time()
@@ -546,11 +632,20 @@ def main():
                        "what": "the reference port (oracle/) in eager fp32 on this GPU, allow_tf32=False: stock index_select / index_add_ / cuBLAS path, featurized graphs resident",
                        "sample": "6 steps after 3 warm-up over the pool's first two batches (wall clock with device sync)"}
 
+    graphs_captured = len(getattr(stepper, "graphs", {}))
+    config5 = None
+    if world == 1 and not args.no_config5:
+        mark(rank, "config 5 (isolated GVPConvLayer at (100,16)/(32,1))")
+        stepper.close()
+        eager.close()
+        torch.cuda.empty_cache()
+        config5 = config5_block(dev)
+
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, world),
-        "launch_mode": graph_note, "graphs_captured": len(getattr(stepper, "graphs", {})),
+        "launch_mode": graph_note, "graphs_captured": graphs_captured,
         "batches": {"per_rank_real_nodes_edges_atoms_padded_nodes": gathered, "params": opt.numel,
                     "edges_per_s_conv": 2 * edges_real * world / max(ms_total / 1e3, 1e-9),
                     "note": "each rank takes the parallel.shard_by_cost share (equal pair counts, balanced edge totals) of every global batch"},
@@ -563,6 +658,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "reference_gpu": ref_gpu,
+        "config5_gvpconvlayer": config5,
     }
     emit(out)
     finish()

@@ -60,12 +60,24 @@ def _act(code, x):
 
 
 def _act_bwd(code, y, g):
-    """g * act'(.) expressed through the activation OUTPUT y (as csrc/cgvp_reg.cuh::actb)."""
+    """g * act'(.) expressed through the activation OUTPUT y (as csrc/cgvp_reg.cuh::actb), one kernel each."""
     if code == ACT_RELU:
-        return g * (y > 0).to(g.dtype)
+        return torch.ops.aten.threshold_backward(g, y, 0.0)        # g where y > 0
     if code == ACT_SIGMOID:
-        return g * (y * (1 - y))
+        return torch.ops.aten.sigmoid_backward(g, y)               # g * y * (1 - y)
     return g
+
+
+_SQRT_EPS = {}
+
+
+def _clamped_norm(vp):
+    """`_norm_no_nan` over the planes, `sqrt(max(sum_xyz v^2, 1e-8))` (`models/gvp_layers.py:79-86`), as ONE reduction plus a
+    clamp: sqrt is monotonic, so the clamp moves behind it with the bound sqrt(1e-8) (rounded in the working dtype)."""
+    lo = _SQRT_EPS.get(vp.dtype)
+    if lo is None:
+        lo = _SQRT_EPS[vp.dtype] = float(torch.tensor(EPS, dtype=vp.dtype).sqrt())
+    return torch.linalg.vector_norm(vp, dim=0).clamp_(min=lo), lo
 
 
 def _mm3(vp, w_t):
@@ -150,9 +162,9 @@ def _gvp_tail(g, sp, vh):
                 sg = torch.sigmoid(torch.addmm(g.bg, gi, g.wsv.t()))
                 sv["gi"] = gi
             elif sp_.vact != ACT_NONE:                                        # :164-166
-                q2 = (vo * vo).sum(0)
-                sg = _act(sp_.vact, q2.clamp(min=EPS).sqrt())
-                sv["q2"] = q2
+                n2, lo = _clamped_norm(vo)
+                sg = _act(sp_.vact, n2)
+                sv["n2"], sv["lo"] = n2, lo
             v_out = vo if sg is None else vo * sg
             sv["vo"], sv["sg"] = vo, sg
         else:                                                                 # :169-171
@@ -164,15 +176,14 @@ def _gvp_forward(g, s, vp):
     sp_ = g.spec
     if sp_.vi > 0:
         vh = _mm3(vp, g.wh.t())                                               # :151-152
-        q = (vh * vh).sum(0)
-        vn = q.clamp(min=EPS).sqrt()                                          # :153
+        vn, lo = _clamped_norm(vh)                                            # :153
         sp = torch.addmm(g.bs, s, g.ws[:, :sp_.si].t())                       # :154, [s ; vn] never concatenated
         sp.addmm_(vn, g.ws[:, sp_.si:].t())
     else:
-        vh = q = vn = None
+        vh = vn = lo = None
         sp = torch.addmm(g.bs, s, g.ws.t())                                   # :168
     s_out, v_out, sv = _gvp_tail(g, sp, vh)
-    sv["q"], sv["vn"] = q, vn
+    sv["vn"], sv["vn_lo"] = vn, lo
     return s_out, v_out, sv
 
 
@@ -186,17 +197,16 @@ def _gvp_bwd_core(g, sv, gs, gv, grads):
     if sp_.vi > 0 and sp_.vo > 0 and gv is not None:
         vo, sg = sv["vo"], sv["sg"]
         if sp_.has_gate:
-            dot = (gv * vo).sum(0)
-            dg = dot * sg * (1 - sg)
+            dg = torch.ops.aten.sigmoid_backward((gv * vo).sum(0), sg)        # (gv . Vo) sg (1 - sg)
             dvo = gv * sg
             gi = sv["gi"]
-            ds = ds + _act_bwd(sp_.vact, gi, dg @ g.wsv)
+            ds = torch.addmm(ds, dg, g.wsv) if sp_.vact == ACT_NONE else ds + _act_bwd(sp_.vact, gi, dg @ g.wsv)
             grads[WSV].addmm_(dg.t(), gi)
             grads[BG].add_(dg.sum(0))
         elif sp_.vact != ACT_NONE:
             dot = (gv * vo).sum(0)
-            q2 = sv["q2"]
-            t = torch.where(q2 >= EPS, _act_bwd(sp_.vact, sg, dot) / q2.clamp(min=EPS).sqrt(), torch.zeros_like(dot))
+            n2 = sv["n2"]
+            t = (_act_bwd(sp_.vact, sg, dot) / n2).masked_fill_(n2 <= sv["lo"], 0)      # the clamp passes no gradient
             dvo = gv * sg + vo * t
         else:
             dvo = gv
@@ -207,7 +217,7 @@ def _gvp_bwd_core(g, sv, gs, gv, grads):
 
 def _norm_bwd(sv, dvn, dvh):
     """dVh += Vh * dvn / vn where the clamp of `_norm_no_nan` passes."""
-    f = torch.where(sv["q"] >= EPS, dvn / sv["vn"], torch.zeros_like(dvn))
+    f = dvn.div_(sv["vn"]).masked_fill_(sv["vn"] <= sv["vn_lo"], 0)
     t = sv["vh"] * f
     return t if dvh is None else dvh.add_(t)
 
@@ -316,15 +326,14 @@ class _ConvPass:
         vh.add_(self.pv_i.index_select(1, d_))
         if self.ev > 0:
             vh.add_(_mm3(evp_c, self.wh_e.t()))
-        q = (vh * vh).sum(0)
-        vn = q.clamp(min=EPS).sqrt()
+        vn, lo = _clamped_norm(vh)
         sp = self.ps_j.index_select(0, s_)
         sp.add_(self.ps_i.index_select(0, d_))
         if self.es > 0:
             sp.addmm_(es_c, self.ws_e.t())
         sp.addmm_(vn, self.ws_vn.t())
         s, v, sv = _gvp_tail(g0, sp, vh)
-        sv["q"], sv["vn"] = q, vn
+        sv["vn"], sv["vn_lo"] = vn, lo
         outs, saves = [(s, v)], [sv]
         for g in self.g[1:]:
             s, v, sv = _gvp_forward(g, s, v)
