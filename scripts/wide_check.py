@@ -37,7 +37,7 @@ def main():
     if not torch.cuda.is_available():
         return 1
     import pytest
-    rc = pytest.main(["-x", "-q", "-m", "gpu", os.path.join(ROOT, "tests", "test_gpu_wide.py"), "-p", "no:cacheprovider"])
+    rc = pytest.main(["-x", "-q", "-m", "gpu", os.path.join(ROOT, "tests", "test_gpu_wide.py"), "-p", "no:cacheprovider", "--tb=short"])
     put({"stage": "pytest tests/test_gpu_wide.py", "rc": int(rc)})
     if time.time() - T0 > args.budget:
         put({"stage": "stopped", "why": "time budget"})
