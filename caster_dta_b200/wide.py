@@ -86,10 +86,29 @@ def _mm3(vp, w_t):
     return (vp.reshape(3 * r, vp.shape[2]) @ w_t).view(3, r, w_t.shape[1])
 
 
+WGRAD_BLOCK = 2048            # rows per partial product of a weight-gradient GEMM (see _tdot)
+
+
+def _tdot(a, b):
+    """a^T b for a [R, A], b [R, B] with R >> A, B: every weight-gradient GEMM of this module.  The result is one small tile,
+    so a plain GEMM call leaves the whole reduction over R to the one or two CTAs that own it; here the rows are cut into
+    blocks of WGRAD_BLOCK, the blocks' partial products are ONE batched GEMM (a CTA per block) and the partials are summed in
+    block order -- a deterministic split-K."""
+    r = a.shape[0]
+    nb = r // WGRAD_BLOCK
+    if nb < 4:
+        return a.t() @ b
+    m = nb * WGRAD_BLOCK
+    out = torch.bmm(a[:m].reshape(nb, WGRAD_BLOCK, a.shape[1]).transpose(1, 2), b[:m].reshape(nb, WGRAD_BLOCK, b.shape[1])).sum(0)
+    if m < r:
+        out.addmm_(a[m:].t(), b[m:])
+    return out
+
+
 def _mm3_t(ap, bp):
     """sum over planes and rows of a^T b:  [3, R, A], [3, R, B] -> [A, B]  (weight gradients of the vector GEMMs)."""
     r = ap.shape[1]
-    return ap.reshape(3 * r, ap.shape[2]).t() @ bp.reshape(3 * r, bp.shape[2])
+    return _tdot(ap.reshape(3 * r, ap.shape[2]), bp.reshape(3 * r, bp.shape[2]))
 
 
 def _planes(v):
@@ -201,7 +220,7 @@ def _gvp_bwd_core(g, sv, gs, gv, grads):
             dvo = gv * sg
             gi = sv["gi"]
             ds = torch.addmm(ds, dg, g.wsv) if sp_.vact == ACT_NONE else ds + _act_bwd(sp_.vact, gi, dg @ g.wsv)
-            grads[WSV].addmm_(dg.t(), gi)
+            grads[WSV].add_(_tdot(dg, gi))
             grads[BG].add_(dg.sum(0))
         elif sp_.vact != ACT_NONE:
             dot = (gv * vo).sum(0)
@@ -227,14 +246,14 @@ def _gvp_bwd_finish(g, sv, s_in, v_in, ds, dvh, grads, need_dx=True):
     sp_ = g.spec
     grads[BS].add_(ds.sum(0))
     if sp_.vi > 0:
-        grads[WS][:, :sp_.si].addmm_(ds.t(), s_in)
-        grads[WS][:, sp_.si:].addmm_(ds.t(), sv["vn"])
+        grads[WS][:, :sp_.si].add_(_tdot(ds, s_in))
+        grads[WS][:, sp_.si:].add_(_tdot(ds, sv["vn"]))
         dvh = _norm_bwd(sv, ds @ g.ws[:, sp_.si:], dvh)
         grads[WH].add_(_mm3_t(dvh, v_in))
         if not need_dx:
             return None, None
         return ds @ g.ws[:, :sp_.si], _mm3(dvh, g.wh)
-    grads[WS].addmm_(ds.t(), s_in)
+    grads[WS].add_(_tdot(ds, s_in))
     return (ds @ g.ws if need_dx else None), None
 
 
@@ -402,8 +421,8 @@ def conv_backward(prog, plan, x_s, x_v, e_s, e_v, weights, d_out_s, d_out_v):
             ds0, dvh0 = _gvp_bwd_core(g0, sv0, gs, gv, gr0)
             # message GVP 0: edge / norm blocks per edge, node blocks after the per-node reductions below
             if es > 0:
-                gr0[WS][:, ns:ns + es].addmm_(ds0.t(), es_c)
-            gr0[WS][:, 2 * ns + es:].addmm_(ds0.t(), sv0["vn"])
+                gr0[WS][:, ns:ns + es].add_(_tdot(ds0, es_c))
+            gr0[WS][:, 2 * ns + es:].add_(_tdot(ds0, sv0["vn"]))
             dvh0 = _norm_bwd(sv0, ds0 @ cp.ws_vn, dvh0)
             if ev > 0:
                 gr0[WH][:, nv:nv + ev].add_(_mm3_t(dvh0, evp_c))
@@ -431,8 +450,8 @@ def conv_backward(prog, plan, x_s, x_v, e_s, e_v, weights, d_out_s, d_out_v):
         ris, rjs = r_i[:, :so0], r_j[:, :so0]
         d_x_s = ris @ cp.ws_i
         d_x_s.addmm_(rjs, cp.ws_j)
-        gr0[WS][:, :ns].copy_(rjs.t() @ x_s)
-        gr0[WS][:, ns + es:2 * ns + es].copy_(ris.t() @ x_s)
+        gr0[WS][:, :ns].copy_(_tdot(rjs, x_s))
+        gr0[WS][:, ns + es:2 * ns + es].copy_(_tdot(ris, x_s))
         gr0[BS].copy_(ris.sum(0))                                  # every edge has exactly one target
         rvi = r_i[:, so0:so0 + 3 * h0].reshape(n, 3, h0).permute(1, 0, 2).contiguous()
         rvj = r_j[:, so0:so0 + 3 * h0].reshape(n, 3, h0).permute(1, 0, 2).contiguous()

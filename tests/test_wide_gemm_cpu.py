@@ -49,6 +49,7 @@ def _substitute_primitive(monkeypatch):
     monkeypatch.setattr(wide, "_segsum", segsum_reference)
     monkeypatch.setattr(wide, "ENABLED", True)
     monkeypatch.setattr(wide, "MIN_DIM", 1)
+    monkeypatch.setattr(wide, "WGRAD_BLOCK", 16)      # edge-level weight gradients take the blocked path, node-level ones the plain one
 
 
 def layer_case(n, e, nd, ed, seed, hub=False, isolated=False):
@@ -303,3 +304,13 @@ def test_rows_function_backward_routes_wide_node_update(monkeypatch):
         assert torch.equal(got[11 + i], want["ln"][i])
     for i in range(len(w)):
         assert torch.equal(got[15 + i], want["dw"][i])
+
+
+def test_blocked_weight_gradient_product():
+    """`_tdot`: the blocked (batched-GEMM) a^T b equals the plain product, ragged tail included."""
+    g = torch.Generator().manual_seed(0)
+    for r in (3, 64, 70, 127):
+        a, b = torch.randn(r, 5, generator=g, dtype=torch.float64), torch.randn(r, 7, generator=g, dtype=torch.float64)
+        close(wide._tdot(a, b), a.t() @ b, f"rows {r}", tol=1e-13)
+    a = torch.randn(100, 12, generator=g, dtype=torch.float64)
+    close(wide._tdot(a[:, 2:9], a[:, :5]), a[:, 2:9].t() @ a[:, :5], "strided operands", tol=1e-13)
