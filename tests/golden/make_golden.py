@@ -13,6 +13,8 @@ the inputs / parameters / outputs / gradients are written as `*.npz`.  These fil
 Fixtures:
   gvp_units.npz      GVP (8 activation/gate/shape variants), LayerNorm, GVPConv, GVPConvLayer (+node_mask,
                      +autoregressive) -- outputs and autograd gradients in fp64.
+  layer_wide.npz     ONE GVPConvLayer at the BASELINE config-5 dims, nodes (100,16) / edges (32,1), vector_gate, (ReLU, None),
+                     mean aggregation (171 909 parameters, stored as fp32): outputs and every gradient in fp64.
   featurizer.npz     compute_residue_edge_features + construct_graph on synthetic backbones, 6 settings.
   lba_checkpoint.npz protein-GNN slice of the shipped checkpoint (15 117 parameters) + a small synthetic batch
                      (radius 4 A and kNN-10 graphs) + the reference embeddings [N,64].
@@ -225,6 +227,41 @@ def make_gvp_units():
         put_state(store, name, m)
     np.savez_compressed(os.path.join(HERE, "gvp_units.npz"), **store)
     print("gvp_units.npz", len(store), "arrays")
+
+
+def make_layer_wide():
+    """BASELINE config 5: `GVPConvLayer(vector_gate=True, activations=(ReLU, None), aggr='mean', drop_rate=0)`
+    at nodes (100,16), edges (32,1) on a small random multigraph (isolated nodes, a zero vector row)."""
+    store = {}
+    g = torch.Generator().manual_seed(95)
+    nn_, ee = 48, 360
+    nd, ed = (100, 16), (32, 1)
+    ei = rand_graph(nn_, ee, g)
+    torch.manual_seed(17)
+    m = fix_module(ref.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean")).eval()
+    with torch.no_grad():
+        for k in range(2):
+            m.norm[k].scalar_norm.weight.copy_(f32(1 + 0.2 * torch.randn(nd[0])))
+            m.norm[k].scalar_norm.bias.copy_(f32(0.2 * torch.randn(nd[0])))
+    s = f32(torch.randn(nn_, nd[0], generator=g)).requires_grad_()
+    v = f32(torch.randn(nn_, nd[1], 3, generator=g)).requires_grad_()
+    v.data[3] = 0.0
+    es = f32(torch.randn(ee, ed[0], generator=g)).requires_grad_()
+    ev = f32(torch.randn(ee, ed[1], 3, generator=g)).requires_grad_()
+    outs = list(m((s, v), ei, (es, ev)))
+    cots = [f32(torch.randn(o.shape, generator=g)) for o in outs]
+    named = [(a, b) for a, b in m.named_parameters() if b.numel()]
+    gr = grads_of(outs, cots, [s, v, es, ev] + [b for _, b in named])
+    name = "layer_wide"
+    put(store, name, node_dims=nd, edge_dims=ed, aggr="mean", n_feedforward=2, autoregressive=0, edge_index=ei,
+        s=s, v=v, es=es, ev=ev, out_s=outs[0], out_v=outs[1], cot_s=cots[0], cot_v=cots[1],
+        grad_s=gr[0], grad_v=gr[1], grad_es=gr[2], grad_ev=gr[3])
+    for k, t in m.state_dict().items():                                 # fp32-representable by construction: store as fp32
+        store[f"{name}/param/{k}"] = t.detach().float().numpy()
+    for (pn, _), gp in zip(named, gr[4:]):
+        store[f"{name}/grad_param/{pn}"] = gp.numpy()
+    np.savez_compressed(os.path.join(HERE, "layer_wide.npz"), **store)
+    print("layer_wide.npz", len(store), "arrays,", sum(p.numel() for p in m.parameters()), "parameters")
 
 
 def reference_graph(coords, idents, thresh, ttype, keep_self):
@@ -452,7 +489,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "joint_checkpoint":
         make_joint_checkpoint()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "layer_wide":
+        make_layer_wide()
+        sys.exit(0)
     make_gvp_units()
+    make_layer_wide()
     make_featurizer()
     make_lba_checkpoint()
     make_joint_small()

@@ -77,9 +77,10 @@ def test_gvp_conv(name):
                  {k: t for k, t in p.items() if t.numel()})
 
 
-@pytest.mark.parametrize("name", ["layer_mean", "layer_sum", "layer_ff1", "layer_mask", "layer_autoreg"])
+@pytest.mark.parametrize("name", ["layer_mean", "layer_sum", "layer_ff1", "layer_mask", "layer_autoreg", "layer_wide"])
 def test_gvp_conv_layer(name):
-    c = case(golden("gvp_units"), name)
+    # layer_wide: BASELINE config-5 dims, nodes (100,16) / edges (32,1), its own fixture file
+    c = case(golden("layer_wide" if name == "layer_wide" else "gvp_units"), name)
     p = {k: _leaf(v) if v.numel() else v for k, v in c["param"].items()}
     s, v, es, ev = _leaf(c["s"]), _leaf(c["v"]), _leaf(c["es"]), _leaf(c["ev"])
     aggr = none_str(c["aggr"]) or "mean"

@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from caster_dta_b200 import modules, ops, wide
+from helpers import case, golden
 from oracle import gvp_oracle
 
 TOL = 1e-10
@@ -314,3 +315,42 @@ def test_blocked_weight_gradient_product():
         close(wide._tdot(a, b), a.t() @ b, f"rows {r}", tol=1e-13)
     a = torch.randn(100, 12, generator=g, dtype=torch.float64)
     close(wide._tdot(a[:, 2:9], a[:, :5]), a[:, 2:9].t() @ a[:, :5], "strided operands", tol=1e-13)
+
+
+def test_layer_against_the_reference_fixture_at_config5_dims():
+    """`tests/golden/layer_wide.npz`: ONE GVPConvLayer at nodes (100,16) / edges (32,1) evaluated by the UNMODIFIED reference
+    (make_golden.py).  The GEMM formulation, composed the way autograd composes it (conv -> node update; node update backward
+    -> conv backward), reproduces the reference's outputs and every gradient in fp64."""
+    c = case(golden("layer_wide"), "layer_wide")
+    nd, ed = (100, 16), (32, 1)
+    p = {k: v.double() for k, v in c["param"].items()}
+    x_s, x_v, e_s, e_v = (c[k].double() for k in ("s", "v", "es", "ev"))
+    ei = c["edge_index"]
+    n = x_s.shape[0]
+    plan = cpu_plan(ei, n)
+    layer = modules.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean")
+    cprog = layer.conv._program(False)
+    rprog = modules._row_program(nd[0], nd[1], tuple(m.spec for m in layer.ff_func), residual_in=True, pre_norm=True,
+                                 post_residual=True, post_norm=True)
+    cw, rw = conv_weights(p, "conv.message_func."), conv_weights(p, "ff_func.", 2)
+    dh = wide.conv_forward(cprog, plan, x_s, x_v, e_s, e_v, cw)
+    t = dict(in_s=x_s, in_v=x_v, h_s=dh[0], h_v=dh[1], in_index=None, types=None, mask0_s=None, mask0_v=None, mask1_s=None,
+             mask1_v=None, ln0_w=p["norm.0.scalar_norm.weight"], ln0_b=p["norm.0.scalar_norm.bias"],
+             ln1_w=p["norm.1.scalar_norm.weight"], ln1_b=p["norm.1.scalar_norm.bias"])
+    out_s, out_v = wide.rows_forward(rprog, t, rw)
+    close(out_s, c["out_s"], "out_s")
+    close(out_v, c["out_v"], "out_v")
+    r = wide.rows_backward(rprog, t, rw, c["cot_s"].double(), c["cot_v"].double())
+    g = wide.conv_backward(cprog, plan, x_s, x_v, e_s, e_v, cw, r["d_h_s"], r["d_h_v"])
+    close(r["d_in_s"] + g[0], c["grad_s"], "grad_s")
+    close(r["d_in_v"] + g[1], c["grad_v"], "grad_v")
+    close(g[2], c["grad_es"], "grad_es")
+    close(g[3], c["grad_ev"], "grad_ev")
+    names = ("wh.weight", "ws.weight", "ws.bias", "wv.weight", "wsv.weight", "wsv.bias")
+    for prefix, grads, count in (("conv.message_func.", g[4], 3), ("ff_func.", r["dw"], 2)):
+        for l in range(count):
+            for j, nm in enumerate(names):
+                close(grads[6 * l + j], c["grad_param"][f"{prefix}{l}.{nm}"], f"grad {prefix}{l}.{nm}")
+    for i, key in enumerate(("norm.0.scalar_norm.weight", "norm.0.scalar_norm.bias", "norm.1.scalar_norm.weight",
+                             "norm.1.scalar_norm.bias")):
+        close(r["ln"][i], c["grad_param"][key], "grad " + key)
