@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-config5", action="store_true", help="skip the isolated GVPConvLayer (100,16)/(32,1) measurement")
+    ap.add_argument("--no-kiba", action="store_true", help="skip the KIBA-shape (BASELINE config 3 shape, 64 pairs/GPU) sub-run")
     ap.add_argument("--max-seconds", type=float, default=900.0, help="abort a run that takes longer than this (watchdog)")
     return ap.parse_args()
 
@@ -369,6 +370,29 @@ def config5_block(dev, edges=1_000_000, iters=5):
     return res
 
 
+def kiba_shape_subrun(args):
+    """BASELINE config 3's shape beside the headline (rank 0, N = 1): the same benchmark in a CHILD process with
+    `--shape kiba --pairs 64` (proteins up to 2 000 residues, N ~ 46 k, E ~ 1.4 M per step).  A child, so that nothing it does
+    can touch the headline measurement; never raises."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--shape", "kiba", "--pairs", "64",
+           "--steps", str(max(3, min(args.steps, 20))), "--warmup", str(max(3, min(args.warmup, 5))), "--pool", str(args.pool),
+           "--no-cpu-baseline", "--no-reference-gpu", "--no-config5", "--no-kiba", "--max-seconds", "240"]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"child exited {r.returncode}", "stderr_tail": r.stderr[-300:]}
+        d = json.loads(lines[-1])
+        roof = d.get("roofline") or {}
+        return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
+                "e2e": d.get("e2e"), "config": d["config"], "launch_mode": d.get("launch_mode"),
+                "graphs_captured": d.get("graphs_captured"), "batches": d.get("batches"), "clocks": d.get("clocks"),
+                "kernel_ms_per_step": roof.get("kernel_ms_per_step"), "dominant_kernel": roof.get("kernel"),
+                "roofline_frac": roof.get("frac")}
+    except Exception as exc:                                           # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
+
 _T0 = time.time()
 
 
@@ -668,6 +692,11 @@ def main():
         torch.cuda.empty_cache()
         config5 = config5_block(dev)
 
+    kiba = None
+    if world == 1 and args.shape == "davis" and not args.no_kiba:
+        mark(rank, "KIBA-shape sub-run (config 3 shape, child process)")
+        kiba = kiba_shape_subrun(args)
+
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -686,6 +715,7 @@ def main():
         "cpu_baseline": cpu,
         "reference_gpu": ref_gpu,
         "config5_gvpconvlayer": config5,
+        "config3_kiba_shape_1gpu": kiba,
     }
     emit(out)
     finish()
