@@ -339,6 +339,18 @@ def config5_block(dev, edges=1_000_000, iters=5):
         except Exception as exc:                                       # noqa: BLE001
             res["tcgen05_bf16_forward_vs_fp32_forward"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
         del ei, data
+        # one larger point of the training path (chunking keeps the intermediates bounded: the time should scale with E)
+        try:
+            ei, n, e, data = make(10 * edges)
+            wide.set_enabled(True)
+            torch.cuda.reset_peak_memory_stats(dev)
+            ms = timed(ei, data, True, 2)
+            res["fwd_bwd_fp32_gemm_10x_edges"] = {"edges": e, "ms": ms, "edges_per_s": e / (ms * 1e-3),
+                                                  "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+        except Exception as exc:                                       # noqa: BLE001
+            res["fwd_bwd_fp32_gemm_10x_edges"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+        ei = data = None
+        torch.cuda.empty_cache()
         # the generic tile kernels (the only training path of these dims before wide.py), on a graph they finish quickly
         ei, n, e, data = make(60_000)
         small = {"edges": e}

@@ -5,12 +5,16 @@ happens in `libcastergvp.so`.  Every call is enqueued on the current CUDA stream
 """
 import ctypes as C
 import functools
+import os
 import weakref
 
 import torch
 
 from . import _lib, wide
 from ._lib import lib, check
+
+
+DEBUG_CHECKS = os.environ.get("CGVP_DEBUG", "0") == "1"     # index-range checks with device syncs (debugging aid)
 
 
 def _stream():
@@ -143,6 +147,11 @@ class GraphPlan:
         ei = edge_index.detach().contiguous().long()
         dev = ei.device
         self.E, self.N = int(ei.shape[1]), int(num_nodes)
+        if DEBUG_CHECKS and self.E and not torch.cuda.is_current_stream_capturing():
+            # the kernels trust the indices (as PyG's gather does); CGVP_DEBUG=1 checks them here, at the cost of a device sync
+            lo, hi = int(ei.min()), int(ei.max())
+            if lo < 0 or hi >= self.N:
+                raise ValueError(f"edge_index holds node ids in [{lo}, {hi}] but the graph has {self.N} nodes")
         i32 = dict(dtype=torch.int32, device=dev)
         self.perm = torch.empty(self.E, **i32)
         self.src = torch.empty(self.E, **i32)
