@@ -134,36 +134,18 @@ def test_wide_conv_tensor_core_mode_backward():
     assert_close(out[1], ref[1], 1e-2, "V")
     # Gradients: the backward differentiates its own TF32 recompute of the message chain.  At 2^-11 operand precision a ReLU
     # pre-activation near zero takes the other branch on ~1e-3 of the elements, i.e. in a noticeable share of the 200-element
-    # edge rows (first GPU run: 1 % of the d(edge scalars) rows beyond 3e-2, profiles/r2_wide_check_first_gpu_run.log), so the
-    # bound here is an aggregate one: every gradient tensor within 20 % in L2 and finite.  The fp32 mode carries the tight
-    # per-row bounds (tests above).
-    def l2_close(a, b, what):
+    # edge rows (first GPU run: 1.0 % of the d(edge scalars) rows beyond 3e-2, profiles/r2_wide_check_first_gpu_run.log; a CPU
+    # emulation that rounds every GEMM operand to TF32 gives 1.04 % on this very case, with L2-relative errors of 0.6-2.5 % for
+    # the per-row gradients and <= 0.11 % for the parameter gradients).  Aggregate bounds, ~3x / ~18x above those: per-row
+    # gradients within 8 % in L2, parameter gradients within 2 %.  The fp32 mode carries the tight per-row bounds (tests above).
+    def l2_close(a, b, what, bound):
         a64, b64 = a.detach().double().cpu(), b.detach().double().cpu()
         assert torch.isfinite(a64).all(), f"{what}: non-finite values"
         rel = float((a64 - b64).norm() / b64.norm().clamp(min=1e-30))
-        assert rel <= 0.2, f"{what}: L2-relative error {rel:.3e}"
+        assert rel <= bound, f"{what}: L2-relative error {rel:.3e} > {bound}"
 
     for t, r, k in zip(leaves, l64, ("grad_s", "grad_v", "grad_es", "grad_ev")):
-        l2_close(t.grad, r.grad, k)
+        l2_close(t.grad, r.grad, k, 0.08)
     for name, prm in conv.named_parameters():
         if prm.numel():
-            l2_close(prm.grad, p64["conv." + name].grad, "grad " + name)
-
-
-def test_wide_layer_against_the_reference_fixture(wide_mode):
-    """`tests/golden/layer_wide.npz`: one GVPConvLayer at config-5 dims evaluated by the unmodified reference in fp64."""
-    import caster_dta_b200 as cg
-    c = case(golden("layer_wide"), "layer_wide")
-    nd, ed = (100, 16), (32, 1)
-    m = cg.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean")
-    m.load_state_dict({k: v.float() for k, v in c["param"].items()}, strict=True)
-    m.to(DEV).eval()
-    leaves = [c[k].float().to(DEV).requires_grad_() for k in ("s", "v", "es", "ev")]
-    out = m((leaves[0], leaves[1]), c["edge_index"].to(DEV), (leaves[2], leaves[3]))
-    assert_close(out[0], c["out_s"], TOL, f"s [{wide_mode}]")
-    assert_close(out[1], c["out_v"], TOL, f"V [{wide_mode}]")
-    ((out[0] * c["cot_s"].float().to(DEV)).sum() + (out[1] * c["cot_v"].float().to(DEV)).sum()).backward()
-    for t, k in zip(leaves, ("grad_s", "grad_v", "grad_es", "grad_ev")):
-        assert_rows_close(t.grad, c[k], TOL, f"{k} [{wide_mode}]", atol=1e-6)
-    named = {k: q.grad for k, q in m.named_parameters() if q.numel()}
-    assert_param_grads_close(named, {k: c["grad_param"][k] for k in named}, f"[{wide_mode}]")
+            l2_close(prm.grad, p64["conv." + name].grad, "grad " + name, 0.02)
