@@ -319,21 +319,6 @@ def config5_block(dev, edges=1_000_000, iters=5):
             finally:
                 _lib.set_tensor_cores(False)
         res["modes"] = modes
-        # where the training path's device time goes: kernel shares of ONE forward + backward under the torch profiler (CUPTI;
-        # shares only -- the timings above are taken without it)
-        try:
-            from torch.profiler import ProfilerActivity, profile
-            wide.set_enabled(True)
-            with profile(activities=[ProfilerActivity.CUDA]) as tp:
-                run(ei, data, True)
-                torch.cuda.synchronize()
-            ev = [(k.key, getattr(k, "device_time_total", None) or getattr(k, "cuda_time_total", 0.0), k.count) for k in tp.key_averages()]
-            total = sum(t for _, t, _ in ev) or 1.0
-            ev.sort(key=lambda x: -x[1])
-            res["fwd_bwd_fp32_gemm_kernel_shares"] = {"kernels": len(ev), "launches": int(sum(c for _, _, c in ev)),
-                                                      "top": [{"kernel": k[:90], "share": t / total, "launches": int(c)} for k, t, c in ev[:10]]}
-        except Exception as exc:                                       # noqa: BLE001
-            res["fwd_bwd_fp32_gemm_kernel_shares"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
         # parity at the benchmarked size: tcgen05 bf16 forward against the fp32 GEMM forward of the same layer (<= 1e-2 mode)
         try:
             outs = {}
