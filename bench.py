@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "config5"])
     ap.add_argument("--shape", default="davis")
     ap.add_argument("--pairs", type=int, default=PAIRS, help="pairs per GPU and step (the sampler's max batch size)")
     ap.add_argument("--pool", type=int, default=8, help="distinct batches the steps cycle over")
@@ -382,27 +382,34 @@ def config5_block(dev, edges=1_000_000, iters=5):
     return res
 
 
-def kiba_shape_subrun(args):
-    """BASELINE config 3's shape beside the headline (rank 0, N = 1): the same benchmark in a CHILD process with
-    `--shape kiba --pairs 64` (proteins up to 2 000 residues, N ~ 46 k, E ~ 1.4 M per step).  A child, so that nothing it does
-    can touch the headline measurement; never raises."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--shape", "kiba", "--pairs", "64",
-           "--steps", str(max(3, min(args.steps, 20))), "--warmup", str(max(3, min(args.warmup, 5))), "--pool", str(args.pool),
-           "--no-cpu-baseline", "--no-reference-gpu", "--no-config5", "--no-kiba", "--max-seconds", "240"]
+def run_child(extra, timeout):
+    """Run this script again in a CHILD process and return its ONE JSON line (or an {"error": ...} dict): the extras measured
+    beside the headline must not be able to crash, hang or poison the CUDA context of the process that prints the line."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1"] + list(extra)
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
         lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": f"child exited {r.returncode}", "stderr_tail": r.stderr[-300:]}
-        d = json.loads(lines[-1])
-        roof = d.get("roofline") or {}
-        return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
-                "e2e": d.get("e2e"), "config": d["config"], "launch_mode": d.get("launch_mode"),
-                "graphs_captured": d.get("graphs_captured"), "batches": d.get("batches"), "clocks": d.get("clocks"),
-                "kernel_ms_per_step": roof.get("kernel_ms_per_step"), "dominant_kernel": roof.get("kernel"),
-                "roofline_frac": roof.get("frac")}
+        return json.loads(lines[-1])
     except Exception as exc:                                           # noqa: BLE001
         return {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
+
+def kiba_shape_subrun(args):
+    """BASELINE config 3's shape beside the headline (rank 0, N = 1): the same benchmark in a child process with
+    `--shape kiba --pairs 64` (proteins up to 2 000 residues, N ~ 46 k, E ~ 1.4 M per step).  Never raises."""
+    d = run_child(["--shape", "kiba", "--pairs", "64", "--steps", str(max(3, min(args.steps, 20))),
+                   "--warmup", str(max(3, min(args.warmup, 5))), "--pool", str(args.pool), "--no-cpu-baseline",
+                   "--no-reference-gpu", "--no-config5", "--no-kiba", "--max-seconds", "240"], timeout=300)
+    if "error" in d:
+        return d
+    roof = d.get("roofline") or {}
+    return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
+            "e2e": d.get("e2e"), "config": d["config"], "launch_mode": d.get("launch_mode"),
+            "graphs_captured": d.get("graphs_captured"), "batches": d.get("batches"), "clocks": d.get("clocks"),
+            "kernel_ms_per_step": roof.get("kernel_ms_per_step"), "dominant_kernel": roof.get("kernel"),
+            "roofline_frac": roof.get("frac")}
 
 
 _T0 = time.time()
@@ -432,6 +439,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     arm_watchdog(rank, args.max_seconds)
 
+    if args.impl == "config5":                       # child mode of the default run (see run_child): the config-5 block alone
+        if rank == 0:
+            if not torch.cuda.is_available():
+                emit({"error": "no CUDA device"})
+                return
+            torch.cuda.set_device(local)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            emit(config5_block(torch.device("cuda", local)))
+        return
     if args.impl != "ours":
         if rank == 0:
             reference_arm(args, world)
@@ -698,11 +714,11 @@ def main():
     graphs_captured = len(getattr(stepper, "graphs", {}))
     config5 = None
     if world == 1 and not args.no_config5:
-        mark(rank, "config 5 (isolated GVPConvLayer at (100,16)/(32,1))")
+        mark(rank, "config 5 (isolated GVPConvLayer at (100,16)/(32,1), child process)")
         stepper.close()
         eager.close()
         torch.cuda.empty_cache()
-        config5 = config5_block(dev)
+        config5 = run_child(["--impl", "config5", "--max-seconds", "240"], timeout=300)
 
     kiba = None
     if world == 1 and args.shape == "davis" and not args.no_kiba:
@@ -730,7 +746,13 @@ def main():
         "config3_kiba_shape_1gpu": kiba,
     }
     emit(out)
-    finish()
+    try:
+        finish()
+    except Exception:                                                  # noqa: BLE001  -- the line is out: leave cleanly
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
