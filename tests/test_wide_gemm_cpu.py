@@ -354,3 +354,50 @@ def test_layer_against_the_reference_fixture_at_config5_dims():
     for i, key in enumerate(("norm.0.scalar_norm.weight", "norm.0.scalar_norm.bias", "norm.1.scalar_norm.weight",
                              "norm.1.scalar_norm.bias")):
         close(r["ln"][i], c["grad_param"][key], "grad " + key)
+
+
+def test_plain_gvp_and_layernorm_programs_match_oracle():
+    """The stand-alone `GVP` and `LayerNorm` modules at wide dims are row programs too (one GVP, no norms / only the norm)."""
+    n, nd = 23, (20, 5)
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(n, nd[0], generator=g, dtype=torch.float64), torch.randn(n, nd[1], 3, generator=g, dtype=torch.float64))
+    x[1][2] = 0
+    cs, cv = torch.randn(n, 9, generator=g, dtype=torch.float64), torch.randn(n, 4, 3, generator=g, dtype=torch.float64)
+    # GVP (20,5) -> (9,4), reference defaults: (relu, sigmoid), no gate
+    p = gvp_oracle.init_gvp_params({}, "g.", nd, (9, 4), vector_gate=False, gen=g, dtype=torch.float64)
+    gv = modules.GVP(nd, (9, 4))
+    prog = modules._row_program(nd[0], nd[1], (gv.spec,))
+    w = [p["g.wh.weight"], p["g.ws.weight"], p["g.ws.bias"], p["g.wv.weight"], None, None]
+    t = dict(in_s=x[0], in_v=x[1], in_index=None, types=None)
+    assert wide.rows_supported(prog, t)
+    leaves = [q.clone().requires_grad_() for q in x]
+    pl = {k: v.clone().requires_grad_(v.numel() > 0) for k, v in p.items()}
+    ref = gvp_oracle.gvp(pl, "g.", (leaves[0], leaves[1]), "relu", "sigmoid", False)
+    out = wide.rows_forward(prog, t, w)
+    close(out[0], ref[0].detach(), "gvp s")
+    close(out[1], ref[1].detach(), "gvp V")
+    ((ref[0] * cs).sum() + (ref[1] * cv).sum()).backward()
+    got = wide.rows_backward(prog, t, w, cs, cv)
+    close(got["d_in_s"], leaves[0].grad, "gvp d_in_s")
+    close(got["d_in_v"], leaves[1].grad, "gvp d_in_v")
+    for j, nm in enumerate(("wh.weight", "ws.weight", "ws.bias", "wv.weight")):
+        close(got["dw"][j], pl["g." + nm].grad, "gvp grad " + nm)
+    assert got["dw"][4] is None and got["dw"][5] is None and got["d_h_s"] is None
+    # LayerNorm only
+    p = gvp_oracle.init_layer_norm_params({}, "ln.", nd[0], g, torch.float64)
+    prog = modules._row_program(nd[0], nd[1], (), pre_norm=True)
+    t = dict(in_s=x[0], in_v=x[1], in_index=None, types=None, ln0_w=p["ln.scalar_norm.weight"], ln0_b=p["ln.scalar_norm.bias"])
+    assert wide.rows_supported(prog, t)
+    leaves = [q.clone().requires_grad_() for q in x]
+    pl = {k: v.clone().requires_grad_() for k, v in p.items()}
+    ref = gvp_oracle.layer_norm(pl, "ln.", (leaves[0], leaves[1]))
+    out = wide.rows_forward(prog, t, [])
+    close(out[0], ref[0].detach(), "ln s")
+    close(out[1], ref[1].detach(), "ln V")
+    cs, cv = torch.randn_like(x[0]), torch.randn_like(x[1])
+    ((ref[0] * cs).sum() + (ref[1] * cv).sum()).backward()
+    got = wide.rows_backward(prog, t, [], cs, cv)
+    close(got["d_in_s"], leaves[0].grad, "ln d_in_s")
+    close(got["d_in_v"], leaves[1].grad, "ln d_in_v")
+    close(got["ln"][0], pl["ln.scalar_norm.weight"].grad, "ln d_w")
+    close(got["ln"][1], pl["ln.scalar_norm.bias"].grad, "ln d_b")
