@@ -401,3 +401,38 @@ def test_plain_gvp_and_layernorm_programs_match_oracle():
     close(got["d_in_v"], leaves[1].grad, "ln d_in_v")
     close(got["ln"][0], pl["ln.scalar_norm.weight"].grad, "ln d_w")
     close(got["ln"][1], pl["ln.scalar_norm.bias"].grad, "ln d_b")
+
+
+def test_conv_random_dims_sweep(monkeypatch):
+    """Seeded sweep over random dims / graphs / chunk sizes / aggregations: forward and every gradient against the oracle."""
+    rng = torch.Generator().manual_seed(2024)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))
+    for trial in range(12):
+        nd, ed = (ri(1, 24), ri(1, 6)), (ri(0, 9), ri(0, 3))
+        n, e = ri(5, 40), ri(1, 200)
+        aggr = ("mean", "sum")[trial % 2]
+        monkeypatch.setattr(wide, "CHUNK_EDGES", ri(1, 64))
+        monkeypatch.setattr(wide, "WGRAD_BLOCK", ri(2, 32))
+        p, ei, x, ea = layer_case(n, e, nd, ed, seed=1000 + trial, hub=trial % 3 == 0, isolated=n > 6)
+        prog = conv_program(nd, ed, aggr)
+        assert wide.conv_supported(prog)
+        plan = cpu_plan(ei, n)
+        w = conv_weights(p, "conv.message_func.")
+        out = wide.conv_forward(prog, plan, x[0], x[1], ea[0], ea[1], w)
+        leaves = [t.clone().requires_grad_() for t in (x[0], x[1], ea[0], ea[1])]
+        pl = {k: v.clone().requires_grad_(v.numel() > 0) for k, v in p.items()}
+        ref = gvp_oracle.gvp_conv(pl, "conv.", (leaves[0], leaves[1]), ei, (leaves[2], leaves[3]), aggr=aggr, scalar_act="relu",
+                                  vector_act=None, vector_gate=True)
+        tag = f"trial {trial} nd={nd} ed={ed} n={n} e={e} {aggr}"
+        close(out[0], ref[0].detach(), tag + " out_s")
+        close(out[1], ref[1].detach(), tag + " out_v")
+        cs, cv = torch.randn(ref[0].shape, generator=rng, dtype=torch.float64), torch.randn(ref[1].shape, generator=rng, dtype=torch.float64)
+        ((ref[0] * cs).sum() + (ref[1] * cv).sum()).backward()
+        got = wide.conv_backward(prog, plan, x[0], x[1], ea[0], ea[1], w, cs, cv)
+        zero = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
+        for g_, leaf, name in zip(got[:4], leaves, ("d_x_s", "d_x_v", "d_e_s", "d_e_v")):
+            close(g_, zero(leaf), tag + " " + name)
+        names = ("wh.weight", "ws.weight", "ws.bias", "wv.weight", "wsv.weight", "wsv.bias")
+        for l in range(3):
+            for j, nm in enumerate(names):
+                close(got[4][6 * l + j], zero(pl[f"conv.message_func.{l}.{nm}"]), f"{tag} grad {l}.{nm}")
