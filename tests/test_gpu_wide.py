@@ -149,3 +149,22 @@ def test_wide_conv_tensor_core_mode_backward():
     for name, prm in conv.named_parameters():
         if prm.numel():
             l2_close(prm.grad, p64["conv." + name].grad, "grad " + name, 0.02)
+
+
+def test_wide_layer_against_the_reference_fixture(wide_mode):
+    """`tests/golden/layer_wide.npz`: one GVPConvLayer at config-5 dims evaluated by the unmodified reference in fp64."""
+    import caster_dta_b200 as cg
+    c = case(golden("layer_wide"), "layer_wide")
+    nd, ed = (100, 16), (32, 1)
+    m = cg.GVPConvLayer(nd, ed, drop_rate=0.0, activations=(F.relu, None), vector_gate=True, aggr="mean")
+    m.load_state_dict({k: v.float() for k, v in c["param"].items()}, strict=True)
+    m.to(DEV).eval()
+    leaves = [c[k].float().to(DEV).requires_grad_() for k in ("s", "v", "es", "ev")]
+    out = m((leaves[0], leaves[1]), c["edge_index"].to(DEV), (leaves[2], leaves[3]))
+    assert_close(out[0], c["out_s"], TOL, f"s [{wide_mode}]")
+    assert_close(out[1], c["out_v"], TOL, f"V [{wide_mode}]")
+    ((out[0] * c["cot_s"].float().to(DEV)).sum() + (out[1] * c["cot_v"].float().to(DEV)).sum()).backward()
+    for t, k in zip(leaves, ("grad_s", "grad_v", "grad_es", "grad_ev")):
+        assert_rows_close(t.grad, c[k], TOL, f"{k} [{wide_mode}]", atol=1e-6)
+    named = {k: q.grad for k, q in m.named_parameters() if q.numel()}
+    assert_param_grads_close(named, {k: c["grad_param"][k] for k in named}, f"[{wide_mode}]")
