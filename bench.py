@@ -319,6 +319,28 @@ def config5_block(dev, edges=1_000_000, iters=5):
             finally:
                 _lib.set_tensor_cores(False)
         res["modes"] = modes
+        # the C-ABI segmented reductions inside this training path (aggregation of the [E,148] message rows; R_i / R_j of the
+        # [E,200] backward rows over the target / source CSR views): device time from the library's own event bracketing,
+        # algorithmic bytes = rows read once + node rows written once + the CSR offsets (+ the index array on the source side)
+        try:
+            wide.set_enabled(True)
+            run(ei, data, True)
+            torch.cuda.synchronize()
+            _lib.profile_enable(True)
+            run(ei, data, True)
+            torch.cuda.synchronize()
+            ms, cnt = _lib.profile_collect()["segment_reduce"]
+            _lib.profile_enable(False)
+            wf, wb = 148, 200
+            alg = 4.0 * (e * wf + n * wf + n) + 2 * 4.0 * (e * wb + n * wb + n) + 4.0 * e
+            peak, src = measured_peaks()
+            res["segment_reduce_in_training_path"] = {"launches": cnt, "ms_total": ms, "algorithmic_bytes": alg,
+                                                      "achieved_GBps": alg / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                                                      "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
+                                                      "peak_GBps": peak, "peak_source": src}
+        except Exception as exc:                                       # noqa: BLE001
+            res["segment_reduce_in_training_path"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+            _lib.profile_enable(False)
         # parity at the benchmarked size: tcgen05 bf16 forward against the fp32 GEMM forward of the same layer (<= 1e-2 mode)
         try:
             outs = {}
