@@ -426,12 +426,14 @@ def kiba_shape_subrun(args):
                    "--no-reference-gpu", "--no-config5", "--no-kiba", "--max-seconds", "240"], timeout=300)
     if "error" in d:
         return d
-    roof = d.get("roofline") or {}
+    roof, e2e = d.get("roofline") or {}, d.get("e2e") or {}
+    shapes = ((d.get("batches") or {}).get("per_rank_real_nodes_edges_atoms_padded_nodes") or [[]])[0]
     return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
-            "e2e": d.get("e2e"), "config": d["config"], "launch_mode": d.get("launch_mode"),
-            "graphs_captured": d.get("graphs_captured"), "batches": d.get("batches"), "clocks": d.get("clocks"),
-            "kernel_ms_per_step": roof.get("kernel_ms_per_step"), "dominant_kernel": roof.get("kernel"),
-            "roofline_frac": roof.get("frac")}
+            "e2e": {k: e2e.get(k) for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "config": d["config"], "launch_mode": d.get("launch_mode"), "graphs_captured": d.get("graphs_captured"),
+            "real_nodes_per_batch": [sh[0] for sh in shapes], "real_edges_per_batch": [sh[1] for sh in shapes],
+            "clocks": d.get("clocks"), "kernel_ms_per_step": roof.get("kernel_ms_per_step"),
+            "dominant_kernel": roof.get("kernel"), "roofline_frac": roof.get("frac")}
 
 
 _T0 = time.time()
