@@ -319,6 +319,40 @@ def config5_block(dev, edges=1_000_000, iters=5):
             finally:
                 _lib.set_tensor_cores(False)
         res["modes"] = modes
+        # the bar on the same box: the reference port (oracle/, eager fp32 torch with autograd -- the stock index_select / cat /
+        # cuBLAS / index_add_ path the reference's modules take on a GPU) on the same layer, graph and inputs
+        try:
+            from oracle import gvp_oracle
+            pref = {k: v.detach().clone().requires_grad_(v.numel() > 0) for k, v in layer.state_dict().items()}
+
+            def ref_run(backward):
+                leaves = [t.detach().clone().requires_grad_(backward) for t in data]
+                for v in pref.values():
+                    v.grad = None
+                with torch.set_grad_enabled(backward):
+                    out = gvp_oracle.gvp_conv_layer(pref, "", (leaves[0], leaves[1]), ei, (leaves[2], leaves[3]), aggr="mean",
+                                                    scalar_act="relu", vector_act=None, vector_gate=True)
+                    if backward:
+                        (out[0].square().sum() + out[1].square().sum()).backward()
+
+            refres = {}
+            for name, bwd in (("fwd", False), ("fwd_bwd", True)):
+                torch.cuda.reset_peak_memory_stats(dev)
+                ref_run(bwd)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(3):
+                    ref_run(bwd)
+                b.record()
+                torch.cuda.synchronize()
+                refres[name + "_ms"] = a.elapsed_time(b) / 3
+                refres[name + "_peak_memory_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+            res["reference_port_eager_gpu"] = refres
+            del pref
+        except Exception as exc:                                       # noqa: BLE001
+            res["reference_port_eager_gpu"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+        torch.cuda.empty_cache()
         # the C-ABI segmented reductions inside this training path (aggregation of the [E,148] message rows; R_i / R_j of the
         # [E,200] backward rows over the target / source CSR views): device time from the library's own event bracketing,
         # algorithmic bytes = rows read once + node rows written once + the CSR offsets (+ the index array on the source side)
