@@ -354,11 +354,12 @@ class ConvFunction(torch.autograd.Function):
         dev = x_s.device
         x_s, x_v, e_s, e_v = _f32(x_s), _f32(x_v), _f32(e_s), _f32(e_v)
         ctx.prog, ctx.plan, ctx.saved, ctx.weights = prog, plan, (x_s, x_v, e_s, e_v), weights
-        ctx.wide = wide.conv_supported(prog)
+        ctx.wide, ctx.kept = wide.conv_supported(prog), None
         if ctx.wide and not _lib.TENSOR_CORES:
             # wide dims (config 5), fp32 mode: chunked GEMM formulation (wide.py); the tensor-core mode keeps the fused
             # tcgen05 forward (csrc/conv_tc.cu) and shares the backward below
-            out_s, out_v = wide.conv_forward(prog, plan, x_s, x_v, e_s, e_v, [_f32(w) for w in weights])
+            ctx.kept = [] if any(ctx.needs_input_grad) else None          # training: intermediates for the backward, if they fit
+            out_s, out_v = wide.conv_forward(prog, plan, x_s, x_v, e_s, e_v, [_f32(w) for w in weights], kept=ctx.kept)
             ctx.stash = ctx.arena = ctx.offs = None
             ctx.mark_non_differentiable(*([] if prog.out_v else [out_v]))
             return out_s, out_v
@@ -388,8 +389,9 @@ class ConvFunction(torch.autograd.Function):
         dev = x_s.device
         d_out_s, d_out_v = _f32(d_out_s), _f32(d_out_v)
         if ctx.wide:
+            kept, ctx.kept = ctx.kept, None
             d_x_s, d_x_v, d_e_s, d_e_v, dw = wide.conv_backward(prog, plan, x_s, x_v, e_s, e_v, [_f32(w) for w in ctx.weights],
-                                                                d_out_s, d_out_v)
+                                                                d_out_s, d_out_v, kept=kept)
             return (None, None, d_x_s, d_x_v, d_e_s, d_e_v, *dw)
         d_x_s, d_x_v = torch.empty_like(x_s), torch.empty_like(x_v)
         d_e_s, d_e_v = torch.empty_like(e_s), torch.empty_like(e_v)

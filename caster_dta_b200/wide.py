@@ -43,6 +43,9 @@ LN_EPS = 1e-5     # nn.LayerNorm default, models/gvp_layers.py:229
 ENABLED = os.environ.get("CGVP_WIDE_GEMM", "1") == "1"
 MIN_DIM = 64                  # scalar node channels from which the GEMM formulation takes over
 CHUNK_EDGES = 1 << 18         # edges per chunk (intermediates: ~5 KB per edge at config-5 dims)
+# Training: the forward may leave its per-chunk intermediates for the backward of the same call (no recompute) when all of
+# them fit this budget; larger graphs recompute per chunk, which bounds the memory independently of E.
+STASH_BYTES = int(float(os.environ.get("CGVP_WIDE_STASH_GB", "8")) * 2 ** 30)
 
 
 def set_enabled(on):
@@ -211,7 +214,8 @@ def _gvp_bwd_core(g, sv, gs, gv, grads):
     accumulates the gradients of wv, wsv, bg."""
     sp_ = g.spec
     sp = sv["sp"]
-    ds = _act_bwd(sp_.sact, _act(sp_.sact, sp), gs)
+    # ReLU: the sign of s' is the sign of relu(s'), so the mask comes from s' itself (no recompute of the activation)
+    ds = _act_bwd(sp_.sact, sp if sp_.sact == ACT_RELU else _act(sp_.sact, sp), gs)
     dvh = None
     if sp_.vi > 0 and sp_.vo > 0 and gv is not None:
         vo, sg = sv["vo"], sv["sg"]
@@ -237,8 +241,7 @@ def _gvp_bwd_core(g, sv, gs, gv, grads):
 def _norm_bwd(sv, dvn, dvh):
     """dVh += Vh * dvn / vn where the clamp of `_norm_no_nan` passes."""
     f = dvn.div_(sv["vn"]).masked_fill_(sv["vn"] <= sv["vn_lo"], 0)
-    t = sv["vh"] * f
-    return t if dvh is None else dvh.add_(t)
+    return sv["vh"] * f if dvh is None else dvh.addcmul_(sv["vh"], f)
 
 
 def _gvp_bwd_finish(g, sv, s_in, v_in, ds, dvh, grads, need_dx=True):
@@ -361,9 +364,26 @@ class _ConvPass:
         return outs, saves
 
 
-def conv_forward(prog, plan, x_s, x_v, e_s, e_v, weights):
+def _tensor_bytes(obj, seen):
+    """Bytes of the distinct tensors reachable from a nest of tuples / lists / dicts."""
+    if torch.is_tensor(obj):
+        key = (obj.data_ptr(), obj.numel())
+        if key in seen:
+            return 0
+        seen.add(key)
+        return obj.numel() * obj.element_size()
+    if isinstance(obj, dict):
+        return sum(_tensor_bytes(v, seen) for v in obj.values())
+    if isinstance(obj, (list, tuple)):
+        return sum(_tensor_bytes(v, seen) for v in obj)
+    return 0
+
+
+def conv_forward(prog, plan, x_s, x_v, e_s, e_v, weights, kept=None):
     """(out_s [N, ns], out_v [N, nv, 3]) of the fused GVPConv: chunked GEMM message chain, per-edge message rows, one
-    deterministic segmented reduction over the sorted targets (sum, or mean = / max(in-degree, 1))."""
+    deterministic segmented reduction over the sorted targets (sum, or mean = / max(in-degree, 1)).
+    `kept`: an empty list (training).  If the intermediates of ALL chunks fit STASH_BYTES they are appended to it, one entry
+    per chunk, and `conv_backward(..., kept=kept)` then skips its recompute; otherwise the list stays empty."""
     so, vo = prog.out_s, prog.out_v
     n = int(plan.N)
     if plan.E == 0:
@@ -374,20 +394,27 @@ def conv_forward(prog, plan, x_s, x_v, e_s, e_v, weights):
         msg = x_s.new_empty(cp.E, width)
         if width > so + 3 * vo:
             msg[:, so + 3 * vo:].zero_()
+        keep = kept is not None
         for p0, p1 in cp.chunks():
             es_c, evp_c = cp.edge_rows(p0, p1)
-            outs, _ = cp.forward_chunk(p0, p1, es_c, evp_c)
+            outs, saves = cp.forward_chunk(p0, p1, es_c, evp_c)
             ms, mv = outs[-1]
             msg[p0:p1, :so] = ms
             msg[p0:p1, so:so + 3 * vo].unflatten(1, (vo, 3)).copy_(mv.permute(1, 2, 0))       # _merge layout, :101-109
-            del outs
+            if keep:
+                entry = (es_c, evp_c, outs, saves)
+                if p0 == 0 and _tensor_bytes(entry, set()) / (p1 - p0) * cp.E > STASH_BYTES:
+                    keep = False
+                else:
+                    kept.append(entry)
+            del outs, saves
         out = _segsum(msg, plan.rowptr, None, n, mean=prog.desc.aggr == _lib.AGGR_MEAN)
         return out[:, :so].contiguous(), out[:, so:so + 3 * vo].reshape(n, vo, 3).contiguous()
 
 
-def conv_backward(prog, plan, x_s, x_v, e_s, e_v, weights, d_out_s, d_out_v):
-    """Gradients of `conv_forward`: (d_x_s, d_x_v, d_e_s, d_e_v, [6 weight gradients per message GVP]).  The message
-    chain is recomputed per chunk (nothing of size E is kept between forward and backward)."""
+def conv_backward(prog, plan, x_s, x_v, e_s, e_v, weights, d_out_s, d_out_v, kept=None):
+    """Gradients of `conv_forward`: (d_x_s, d_x_v, d_e_s, d_e_v, [6 weight gradients per message GVP]).  The message chain is
+    recomputed per chunk unless the forward of the same call left its intermediates in `kept` (see `conv_forward`)."""
     n, e = int(plan.N), int(plan.E)
     gvps = [_Gvp(sp, weights[6 * i: 6 * i + 6]) for i, sp in enumerate(prog.gvps)]
     grads = [g.zero_grads() for g in gvps]
@@ -409,10 +436,17 @@ def conv_backward(prog, plan, x_s, x_v, e_s, e_v, weights, d_out_s, d_out_v):
         drows = x_s.new_empty(e, width)
         if width > so0 + 3 * h0:
             drows[:, so0 + 3 * h0:].zero_()
-        for p0, p1 in cp.chunks():
+        chunks = list(cp.chunks())
+        if kept is not None and len(kept) != len(chunks):
+            kept = None
+        for ci, (p0, p1) in enumerate(chunks):
             d_ = cp.dst[p0:p1]
-            es_c, evp_c = cp.edge_rows(p0, p1)
-            outs, saves = cp.forward_chunk(p0, p1, es_c, evp_c)
+            if kept is not None:
+                es_c, evp_c, outs, saves = kept[ci]
+                kept[ci] = None                                    # release the chunk's intermediates as soon as it is done
+            else:
+                es_c, evp_c = cp.edge_rows(p0, p1)
+                outs, saves = cp.forward_chunk(p0, p1, es_c, evp_c)
             gs, gv = d_out_s.index_select(0, d_), dovp.index_select(1, d_)
             for k in range(len(cp.g) - 1, 0, -1):
                 ds, dvh = _gvp_bwd_core(cp.g[k], saves[k], gs, gv, grads[k])

@@ -436,3 +436,29 @@ def test_conv_random_dims_sweep(monkeypatch):
         for l in range(3):
             for j, nm in enumerate(names):
                 close(got[4][6 * l + j], zero(pl[f"conv.message_func.{l}.{nm}"]), f"{tag} grad {l}.{nm}")
+
+
+def test_forward_stash_for_the_backward(monkeypatch):
+    """Training: the forward leaves its per-chunk intermediates when they fit `STASH_BYTES`; the backward then gives the same
+    gradients as with its own recompute (same arithmetic: same bits).  Over budget the list stays empty."""
+    monkeypatch.setattr(wide, "CHUNK_EDGES", 64)
+    n, e, nd, ed = 40, 300, (100, 16), (32, 1)
+    p, ei, x, ea = layer_case(n, e, nd, ed, seed=77, hub=True)
+    prog, plan, w = conv_program(nd, ed, "mean"), cpu_plan(ei, n), conv_weights(p, "conv.message_func.")
+    cs, cv = torch.randn(n, nd[0], dtype=torch.float64), torch.randn(n, nd[1], 3, dtype=torch.float64)
+    ref = wide.conv_backward(prog, plan, x[0], x[1], ea[0], ea[1], w, cs, cv)
+    kept = []
+    out = wide.conv_forward(prog, plan, x[0], x[1], ea[0], ea[1], w, kept=kept)
+    assert len(kept) == 5 and torch.equal(out[0], wide.conv_forward(prog, plan, x[0], x[1], ea[0], ea[1], w)[0])
+    got = wide.conv_backward(prog, plan, x[0], x[1], ea[0], ea[1], w, cs, cv, kept=kept)
+    assert all(k is None for k in kept), "chunks are released as the backward consumes them"
+    for a, b in zip(got[:4], ref[:4]):
+        assert torch.equal(a, b)
+    for a, b in zip(got[4], ref[4]):
+        assert (a is None and b is None) or torch.equal(a, b)
+    monkeypatch.setattr(wide, "STASH_BYTES", 1000)
+    kept = []
+    wide.conv_forward(prog, plan, x[0], x[1], ea[0], ea[1], w, kept=kept)
+    assert kept == []
+    got = wide.conv_backward(prog, plan, x[0], x[1], ea[0], ea[1], w, cs, cv, kept=kept)     # empty list: recompute
+    assert torch.equal(got[0], ref[0])
