@@ -462,3 +462,31 @@ def test_forward_stash_for_the_backward(monkeypatch):
     assert kept == []
     got = wide.conv_backward(prog, plan, x[0], x[1], ea[0], ea[1], w, cs, cv, kept=kept)     # empty list: recompute
     assert torch.equal(got[0], ref[0])
+
+
+def test_properties_rotation_permutation_mean():
+    """SURVEY.md section 4 (iii) for the GEMM formulation: scalar outputs invariant and vector outputs equivariant under a random
+    orthogonal transform (`protein_gnn.py:362`), invariance under a permutation of the edge order, mean = sum / in-degree."""
+    n, e, nd, ed = 30, 240, (100, 16), (32, 1)
+    p, ei, x, ea = layer_case(n, e, nd, ed, seed=31, hub=True, isolated=True)
+    w = conv_weights(p, "conv.message_func.")
+    prog_sum, prog_mean = conv_program(nd, ed, "sum"), conv_program(nd, ed, "mean")
+    plan = cpu_plan(ei, n)
+    base = wide.conv_forward(prog_sum, plan, x[0], x[1], ea[0], ea[1], w)
+    # rotation (+ reflection): V -> V Q^T
+    q, _ = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1)))
+    rot = wide.conv_forward(prog_sum, plan, x[0], x[1] @ q.t(), ea[0], ea[1] @ q.t(), w)
+    close(rot[0], base[0], "scalars are invariant")
+    close(rot[1], base[1] @ q.t(), "vectors are equivariant")
+    # edge permutation
+    perm = torch.randperm(e, generator=torch.Generator().manual_seed(2))
+    ei2 = ei[:, perm]
+    per = wide.conv_forward(prog_sum, cpu_plan(ei2, n), x[0], x[1], ea[0][perm], ea[1][perm], w)
+    close(per[0], base[0], "edge order (s)")
+    close(per[1], base[1], "edge order (V)")
+    # mean vs sum
+    deg = torch.bincount(ei[1], minlength=n).clamp(min=1).double()
+    mean = wide.conv_forward(prog_mean, plan, x[0], x[1], ea[0], ea[1], w)
+    close(mean[0], base[0] / deg.unsqueeze(1), "mean = sum / deg (s)")
+    close(mean[1], base[1] / deg.view(-1, 1, 1), "mean = sum / deg (V)")
+    assert float(base[0][-2:].abs().max()) == 0.0 and float(base[1][-2:].abs().max()) == 0.0, "nodes without in-edges get zeros"
